@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: TCJA-SNN inference samples/s at T=20 on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU reference arm
+
+A "step" is one pass of the hot path (frames on device -> logits on device) over
+one batch of synthetic event frames.  Workload at N GPUs = BASELINE.json
+configs[4] sharded by batch: 8-bit weights, 50 % global magnitude pruning, T=20,
+128x128x2 frames, 512 samples per GPU (4096 at N=8), weak scaling, no collective
+on the hot path (one NCCL all-reduce of the accuracy counters after the timed
+region).  Prints ONE JSON line on rank 0.
+
+The reference itself (JAX/Flax) cannot be installed or imported in this image
+(no jax / flax / ml_collections wheels, no network), so
+`--impl reference` and `cpu_baseline` time the oracle's fp32 restatement of the
+same graph (oracle/ref_snn.py, torch-CPU contractions) on the host cores:
+kind = "port".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+GOP_PER_SAMPLE_T20 = 33.647      # dense-equivalent int8 GOP / sample
+CONV2_GOP_PER_SAMPLE = 2 * 12.080
+METRIC = "TCJA-SNN inference samples/sec (T=20)"
+UNIT = "samples/s"
+
+
+def peaks():
+  path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+  if os.path.exists(path):
+    p = json.load(open(path))
+    return dict(hbm=p["hbm_gbs"], bf16=p["bf16_tflops"], bf16_sus=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                src="measured")
+  return dict(hbm=6650.0, bf16=1590.0, bf16_sus=1400.0, src="fallback")
+
+
+class ClockSampler:
+  Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+       "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+       "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+  def __init__(self, gpu_index: int):
+    self.idx = gpu_index
+    self.proc = None
+    self.path = f"/tmp/snnqp_clocks_{os.getpid()}.csv"
+
+  def start(self):
+    try:
+      self.f = open(self.path, "w")
+      self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                    "-lms", "100", "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+    except Exception:
+      self.proc = None
+
+  def stop(self):
+    out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+    if self.proc is None:
+      return out
+    self.proc.terminate()
+    try:
+      self.proc.wait(5)
+    except Exception:
+      self.proc.kill()
+    self.f.close()
+    sm, mx, reasons = [], [], set()
+    for line in open(self.path):
+      parts = [x.strip() for x in line.split(",")]
+      if len(parts) < 9:
+        continue
+      try:
+        sm.append(float(parts[1])); mx.append(float(parts[2]))
+      except ValueError:
+        continue
+      for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+        if val.lower().startswith("active"):
+          reasons.add(name)
+    if sm:
+      out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+             "samples": len(sm)}
+    try:
+      os.remove(self.path)
+    except OSError:
+      pass
+    return out
+
+
+def cpu_reference_samples_per_s(bits, prune, T, H, sample_B, reps, threads):
+  """The oracle's fp32 restatement of the reference graph on the host cores."""
+  import torch
+  from oracle import ref_snn
+  from snnquantprune_b200 import synthetic
+  torch.set_num_threads(threads)
+  v = synthetic.make_variables(bits=bits, prune_percentage=prune, T=T, H=H, seed=1)
+  fr = synthetic.make_frames(sample_B, T, H, H, seed=0)
+  times = []
+  for _ in range(reps):
+    t0 = time.perf_counter()
+    ref_snn.cextnet_forward(v, fr, bits)
+    times.append(time.perf_counter() - t0)
+  return sample_B / statistics.median(times), times
+
+
+def run_reference(args):
+  rank = int(os.environ.get("RANK", "0"))
+  if rank != 0:
+    return 0
+  threads = os.cpu_count() or 1
+  sample_B = args.ref_batch
+  T, H = args.T, args.H
+  import torch
+  from oracle import ref_snn
+  from snnquantprune_b200 import synthetic
+  torch.set_num_threads(threads)
+  v = synthetic.make_variables(bits=args.bits, prune_percentage=args.prune, T=T, H=H, seed=1)
+  fr = synthetic.make_frames(sample_B, T, H, H, seed=0)
+  for _ in range(args.warmup):
+    ref_snn.cextnet_forward(v, fr[:1], args.bits)
+  t0 = time.perf_counter()
+  for _ in range(args.steps):
+    ref_snn.cextnet_forward(v, fr, args.bits)
+  dt = time.perf_counter() - t0
+  val = sample_B * args.steps / dt
+  sample = (f"{sample_B} samples/step of the same workload (bits={args.bits}, prune={args.prune}, T={T}, "
+            f"{H}x{H}x2), oracle fp32 restatement (torch-CPU conv2d/matmul), {threads} threads")
+  line = {
+      "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+      "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+      "config": workload_config(args, sample_B, 1),
+      "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+      "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+      "gpu_launches": 0,
+      "note": "reference (JAX/Flax) cannot be installed in this image; this is the CPU port of the same graph",
+  }
+  print(json.dumps(line), flush=True)
+  return 0
+
+
+def workload_config(args, per_gpu_batch, n):
+  return {"workload": f"TCJA-SNN CextNet eval forward, {args.bits}-bit DuQ weights, {int(args.prune * 100)}% global "
+                      f"magnitude pruning, T={args.T}, {args.H}x{args.H}x2 synthetic DVS frames "
+                      f"(BASELINE.json configs[4] batch-sharded)",
+          "bits": args.bits, "prune_percentage": args.prune, "T": args.T, "frame": [args.H, args.H, 2],
+          "per_gpu_batch": per_gpu_batch, "global_batch": per_gpu_batch * n, "parallelism": f"dp{n}",
+          "l2_policy": f"inputs larger than L2 ({per_gpu_batch * args.T * args.H * args.H * 2 / 1e6:.0f} MB of frames per GPU per step)"}
+
+
+def run_ours(args):
+  import numpy as np
+  import torch
+  from snnquantprune_b200 import CextNetEngine, pack_cextnet, synthetic, _lib
+  from snnquantprune_b200 import dist as D
+
+  rank, ws, local = D.init("nccl")
+  torch.cuda.set_device(local)
+  dev = torch.device("cuda", local)
+  lib = _lib.lib()
+  if lib.snnqp_device_ok() != 1:
+    raise SystemExit("bench.py needs an sm_100 GPU: " + lib.snnqp_last_error().decode())
+  impl = {"auto": _lib.IMPL_AUTO, "simt": _lib.IMPL_SIMT, "tcgen05": _lib.IMPL_TCGEN05}[args.kernels]
+
+  B, T, H = args.batch, args.T, args.H
+  v = synthetic.make_variables(bits=args.bits, prune_percentage=args.prune, T=T, H=H, seed=1)
+  packed = pack_cextnet(v, args.bits, T, H, device=dev)
+  eng = CextNetEngine(packed, impl=impl, chunk=args.chunk, device=dev)
+  # distinct frames per rank (the shard this rank owns of the global batch)
+  base = synthetic.make_frames(min(B, 64), T, H, H, seed=100 + rank)
+  reps = (B + base.shape[0] - 1) // base.shape[0]
+  host_frames = torch.from_numpy(np.concatenate([base] * reps, 0)[:B]).pin_memory()
+  frames = host_frames.to(dev, non_blocking=True)
+  labels = torch.from_numpy(synthetic.make_labels(B, seed=3 + rank)).to(dev)
+  torch.cuda.synchronize()
+
+  # ---- device-resident timing --------------------------------------------
+  for _ in range(args.warmup):
+    logits = eng.forward(frames)
+  torch.cuda.synchronize()
+  sampler = ClockSampler(local)
+  D.barrier(); torch.cuda.synchronize()
+  if rank == 0:
+    sampler.start()
+  lib.snnqp_launch_count(1)
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for _ in range(args.steps):
+    logits = eng.forward(frames)
+  e1.record()
+  torch.cuda.synchronize(); D.barrier()
+  launches = int(lib.snnqp_launch_count(0))
+  clocks = sampler.stop() if rank == 0 else None
+  ms = e0.elapsed_time(e1)
+  t = torch.tensor([ms], device=dev, dtype=torch.float64)
+  D.reduce_max(t)
+  ms_max = float(t.item())
+  value = B * ws * args.steps / (ms_max / 1e3)
+
+  # ---- end to end: pinned host frames -> H2D -> forward -> logits D2H ------
+  host_logits = torch.empty((B, packed.num_classes), dtype=torch.float32).pin_memory()
+  stage = torch.empty_like(frames)
+  e2e_steps = max(1, min(args.steps, args.e2e_steps))
+  for _ in range(1):
+    stage.copy_(host_frames, non_blocking=True); host_logits.copy_(eng.forward(stage), non_blocking=True)
+  torch.cuda.synchronize(); D.barrier()
+  e0.record()
+  for _ in range(e2e_steps):
+    stage.copy_(host_frames, non_blocking=True)
+    host_logits.copy_(eng.forward(stage), non_blocking=True)
+  e1.record()
+  torch.cuda.synchronize(); D.barrier()
+  t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+  D.reduce_max(t)
+  e2e_value = B * ws * e2e_steps / (float(t.item()) / 1e3)
+
+  # ---- dominant kernel (conv2 block), timed live with CUDA events ----------
+  roof = dominant_kernel_roofline(eng, frames, args, dev)
+
+  # ---- final accuracy reduction: the only collective, outside the timed region
+  out = torch.zeros(2, device=dev, dtype=torch.float32)
+  _lib.check(lib.snnqp_eval_metrics(_lib.ptr(logits), _lib.ptr(labels), B, packed.num_classes, _lib.ptr(out),
+                                    _lib.stream()))
+  cnt = torch.tensor([out[0].item(), out[1].item(), float(B)], device=dev, dtype=torch.float64)
+  D.reduce_sums(cnt)
+
+  if rank == 0:
+    pk = peaks()
+    cpu = None
+    if ws == 1 and not args.no_cpu_baseline:
+      threads = os.cpu_count() or 1
+      val, times = cpu_reference_samples_per_s(args.bits, args.prune, T, H, args.cpu_batch, 2, threads)
+      cpu = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+             "sample": f"{args.cpu_batch} samples of the same workload, median of 2 passes, oracle fp32 restatement "
+                       f"of the reference graph (torch-CPU contractions); the JAX reference cannot run in this image"}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int8 x {0,1}/u8 -> int32 accumulate, fp32 epilogue", "data": "synthetic",
+        "config": workload_config(args, B, ws),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_frames.numel()) * ws,
+                "d2h_bytes_per_step": int(host_logits.numel() * 4) * ws, "steps": e2e_steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "network_roofline": {"bound": "tensor", "achieved": value * GOP_PER_SAMPLE_T20 / 1e3, "unit": "TOP/s",
+                             "peak_nominal_int8": 4500.0, "frac_nominal": value * GOP_PER_SAMPLE_T20 / 1e3 / 4500.0,
+                             "peak_2x_measured_bf16": 2 * pk["bf16_sus"],
+                             "frac_2x_measured_bf16_sustained": value * GOP_PER_SAMPLE_T20 / 1e3 / (2 * pk["bf16_sus"]),
+                             "peaks": pk["src"]},
+        "accuracy_vs_random_labels": cnt[0].item() / cnt[2].item(),
+        "kernels": args.kernels,
+    }
+    print(json.dumps(line), flush=True)
+  D.barrier()
+  return 0
+
+
+def dominant_kernel_roofline(eng, frames, args, dev):
+  """conv2 block (72 % of the MACs): algorithmic int8 OPs per launch / measured
+  launch duration.  Timed alone, back to back, on the launching stream."""
+  import torch
+  from snnquantprune_b200 import _lib
+  L = _lib.lib()
+  pk = eng.pk
+  Bc = min(eng.chunk, frames.shape[0])
+  eng._forward_chunk(frames[:Bc], torch.empty((Bc, pk.num_classes), device=dev))
+  ws = eng._workspace(Bc)
+  lay = pk.convs[1]
+  C, Hh = pk.channels, pk.H // 2
+  p = eng._bp(Bc, Hh, C, C, ws["s1"], ws["s2"], 1)
+  call = lambda: _lib.check(L.snnqp_spiking_conv3x3_fwd(p, _lib.ptr(ws["s1"]), None, _lib.ptr(lay.wq),
+                                                        _lib.ptr(lay.scale), _lib.ptr(lay.bias), _lib.ptr(ws["s2"]),
+                                                        None, None, _lib.stream()))
+  for _ in range(3):
+    call()
+  n = 10
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  torch.cuda.synchronize()
+  e0.record()
+  for _ in range(n):
+    call()
+  e1.record()
+  torch.cuda.synchronize()
+  ms = e0.elapsed_time(e1) / n
+  ops = CONV2_GOP_PER_SAMPLE * 1e9 * Bc * (pk.T / 20.0) * (pk.H / 128.0) ** 2
+  pkp = peaks()
+  achieved = ops / (ms / 1e3) / 1e12
+  peak = 2 * pkp["bf16"]
+  return {"kernel": "conv2 fused block (snnqp_spiking_conv3x3_fwd, 64x64x128->128, T steps inside)",
+          "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+          "traffic": None, "ms_per_launch": ms, "units_per_launch": f"{Bc} samples x T={pk.T}",
+          "peak_source": f"2 x {pkp['src']} bf16 burst (no int8 peak is measured; nominal dense int8 is 4500 TOP/s)",
+          "frac_of_nominal_int8": achieved / 4500.0}
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=5)
+  ap.add_argument("--warmup", type=int, default=3)
+  ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+  ap.add_argument("--kernels", default="auto", choices=["auto", "simt", "tcgen05"])
+  ap.add_argument("--batch", type=int, default=512, help="samples per GPU per step")
+  ap.add_argument("--chunk", type=int, default=16, help="samples per fused launch (keeps activations in L2)")
+  ap.add_argument("--bits", type=int, default=8)
+  ap.add_argument("--prune", type=float, default=0.5)
+  ap.add_argument("--T", type=int, default=20)
+  ap.add_argument("--H", type=int, default=128)
+  ap.add_argument("--e2e-steps", type=int, default=3)
+  ap.add_argument("--cpu-batch", type=int, default=8)
+  ap.add_argument("--ref-batch", type=int, default=8)
+  ap.add_argument("--no-cpu-baseline", action="store_true")
+  args = ap.parse_args()
+  if args.warmup < 3 and args.impl == "ours":
+    args.warmup = 3
+  if args.impl == "reference":
+    return run_reference(args)
+  return run_ours(args)
+
+
+if __name__ == "__main__":
+  sys.exit(main())

@@ -1,0 +1,187 @@
+/* snnqp.h -- C-ABI of the B200-native quantized + pruned spiking-layer forward
+ * pass (drop-in for the hot path of Intelligent-Microsystems-Lab/SNNQuantPrune).
+ *
+ * The reference has no FFI of its own: the path sits behind Flax modules
+ * (citations relative to the reference root):
+ *   DuQ.__call__            quant.py:439-469      -> snnqp_duq_forward / snnqp_pack_*
+ *   prune.__call__          quant.py:475-491      -> (mask argument of the above)
+ *   QuantConv.__call__      flax_qconv.py:94-188  -> snnqp_spiking_conv3x3_fwd (fused
+ *   nn.BatchNorm (eval)     examples/tcja/models.py:101-107    with BN + LIF + pool),
+ *   multi_step_LIF.__call__ spiking_learning.py:404-416        snnqp_qconv3x3_fwd (plain)
+ *   SpikingBlock.__call__   spiking_learning.py:441-472
+ *   QuantDense.__call__     flax_qdense.py:59-106 -> snnqp_spiking_dense_fwd
+ *   TCJA                    examples/tcja/models.py:41-99  -> snnqp_tcja_fwd
+ *   max-pool / flatten      examples/tcja/models.py:145-147,189-190 -> fused / pack-time
+ *   vote                    examples/tcja/models.py:253-255 -> snnqp_vote_fwd
+ *   compute_metrics         examples/train_utils.py:220-225 -> snnqp_eval_metrics
+ * These are the entry points an XLA-FFI custom-call shim binds.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller unless named *_host;
+ *    nothing is retained past the call, nothing is allocated on the hot calls
+ *    (TMA descriptors are cached per device, keyed by pointer + shape);
+ *  - every launch goes on the caller's stream (cudaStream_t passed as void*);
+ *    no host synchronisation;
+ *  - return 0 on success, a SNNQP_ERR_* code otherwise; the message of the last
+ *    failure on this thread is returned by snnqp_last_error();
+ *  - spikes and event counts are uint8 (one byte per neuron, channel-minor:
+ *    [...][H][W][C]); timestep / sample strides are explicit (in bytes for
+ *    uint8 tensors, in elements for float tensors) so both the reference's
+ *    time-major (T,B,...) and batch-major (B,T,...) layouts are accepted;
+ *  - there is NO CPU fallback: every entry point fails with SNNQP_ERR_CUDA if
+ *    no sm_100 device is present.
+ */
+#ifndef SNNQP_H_
+#define SNNQP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNNQP_ABI_VERSION 1
+
+#define SNNQP_OK 0
+#define SNNQP_ERR_INVALID 1      /* bad argument / unsupported shape           */
+#define SNNQP_ERR_CUDA 2         /* CUDA runtime / driver error                */
+#define SNNQP_ERR_UNSUPPORTED 3  /* valid in the reference, outside this path  */
+
+/* kernel implementation selector for the fused blocks */
+#define SNNQP_IMPL_AUTO 0
+#define SNNQP_IMPL_SIMT 1        /* dp4a CUDA-core kernels (bring-up / cross-check) */
+#define SNNQP_IMPL_TCGEN05 2     /* tcgen05.mma.kind::i8 + TMA + TMEM               */
+
+int snnqp_abi_version(void);
+const char *snnqp_last_error(void);
+/* 1 if the current device is compute capability 10.x, else 0. */
+int snnqp_device_ok(void);
+
+/* ---------------------------------------------------------------- pack ---- */
+
+/* DuQ forward followed by prune forward, elementwise, fp32 out
+ * (quant.py:439-469, 475-491).  a, c: device pointers to one float each;
+ * mask may be NULL.  bits == -1 or *a == -1 passes the input through. */
+int snnqp_duq_forward(const float *w, const float *mask, const float *a,
+                      const float *c, int bits, int64_t n, float *out,
+                      void *stream);
+
+/* Integer DuQ level (quant.py:463-467) with the mask applied, same layout as
+ * the input: q[i] = round_half_even(clip(w[i] / *a, -1, 1) * L) * (mask != 0),
+ * L = 2^(bits-1) - 1 (4- and 2-bit levels are stored unpacked in int8). */
+int snnqp_pack_levels(const float *w, const float *mask, const float *a,
+                      int bits, int64_t n, int8_t *q, void *stream);
+
+/* 3x3 HWIO kernel (3,3,cin,cout) -> levels in tile layout [9][cout][cin]
+ * (tap-major, one 128-byte K row per output channel when cin == 128). */
+int snnqp_pack_conv3x3(const float *kernel_hwio, const float *mask,
+                       const float *a, int bits, int cin, int cout, int8_t *wq,
+                       void *stream);
+
+/* (K,N) kernel [dense (in,out); 1-D conv (k*cin,cout); conv1 (18,cout)] ->
+ * levels in layout [N][k_pad], zero padded.  row_perm (nullable, K int32):
+ * packed column r reads kernel row row_perm[r] -- used to fold the reference's
+ * NCHW flatten (examples/tcja/models.py:189-190) into the dense1 weights. */
+int snnqp_pack_matrix(const float *kernel_kn, const float *mask, const float *a,
+                      int bits, int K, int N, const int32_t *row_perm,
+                      int k_pad, int8_t *wq, void *stream);
+
+/* Per-channel folded affine so that v = acc * scale[n] + bias[n]:
+ *   scale[n] = (c / L / extra_div) * gamma[n] / sqrt(var[n] + eps)
+ *   bias[n]  = beta[n] - mean[n] * gamma[n] / sqrt(var[n] + eps)
+ * (DuQ dequant scale quant.py:442,467; eval BatchNorm models.py:101-107),
+ * evaluated in IEEE double and rounded once.  gamma..var NULL => no BN:
+ * scale = c / L / extra_div, bias = 0. */
+int snnqp_fold_affine(const float *c, int bits, double extra_div,
+                      const float *gamma, const float *beta, const float *mean,
+                      const float *var, float eps, int n, float *scale,
+                      float *bias, void *stream);
+
+/* Bitmap of all-zero weight K-slabs for the block-sparse skip path:
+ * nz[tap * (cin/32) + j] = 1 iff wq[tap][:, 32j..32j+31] has a non-zero. */
+int snnqp_conv3x3_slab_bitmap(const int8_t *wq, int cin, int cout,
+                              uint8_t *nz, void *stream);
+
+/* ------------------------------------------------------- fused blocks ---- */
+
+typedef struct snnqp_block_params {
+  int32_t T, B, H, W;      /* timesteps, samples, input height/width (dense: 1,1) */
+  int32_t Cin, Cout;       /* input / output features                            */
+  int64_t x_stride_t, x_stride_b; /* bytes between timesteps / samples of x       */
+  int64_t y_stride_t, y_stride_b; /* bytes between timesteps / samples of spikes  */
+  int64_t att_stride_t, att_stride_b; /* elements, for att[(t,b)][Cin or att_mod] */
+  int32_t att_mod;         /* dense: input k uses att[k % att_mod]; conv: = Cin   */
+  float tau, v_threshold, v_reset; /* multi_step_LIF, spiking_learning.py:390-397 */
+  int32_t pool;            /* 1: fuse the 2x2/2 max-pool (models.py:145-147)      */
+  int32_t impl;            /* SNNQP_IMPL_*                                        */
+} snnqp_block_params;
+
+/* SpikingBlock(QuantConv 3x3 pad 1, BatchNorm, multi_step_LIF) over T steps
+ * with zero initial carry (spiking_learning.py:441-472), optionally followed
+ * by the 2x2 max-pool.
+ *   x       uint8 [T,B,H,W,Cin] via strides (event counts or {0,1} spikes)
+ *   att     NULL, or fp32 per-(t,b,cin) multiplier: input = att * x
+ *           (TCJA output y = x_seq * att, models.py:97)
+ *   wq      int8 [9][Cout][Cin] (Cin==128) or [Cout][32] (Cin==2, k=tap*2+ci)
+ *   scale/bias fp32 [Cout] from snnqp_fold_affine
+ *   spikes  uint8 [T,B,H',W',Cout] via strides, H' = H/2 if pool else H
+ *   u_final NULL or fp32 [B][H][W][Cout]: membrane after the last step
+ *   acc_dump NULL or [T][B][H][W][Cout] contiguous: int32 accumulators
+ *           (fp32 accumulators when att != NULL) -- parity instrumentation. */
+int snnqp_spiking_conv3x3_fwd(const snnqp_block_params *p, const uint8_t *x,
+                              const float *att, const int8_t *wq,
+                              const float *scale, const float *bias,
+                              uint8_t *spikes, float *u_final, void *acc_dump,
+                              void *stream);
+
+/* SpikingBlock(QuantDense, multi_step_LIF), no norm (models.py:200-246).
+ *   x uint8 [T,B,Cin] via strides; wq int8 [Cout][k_pad] with k_pad = Cin
+ *   rounded up to 16; att as above with index k % att_mod. */
+int snnqp_spiking_dense_fwd(const snnqp_block_params *p, const uint8_t *x,
+                            const float *att, const int8_t *wq,
+                            const float *scale, const float *bias,
+                            uint8_t *spikes, float *u_final, void *acc_dump,
+                            void *stream);
+
+/* Plain QuantConv 3x3 forward (no norm / neuron): y fp32 [T,B,H,W,Cout]
+ * contiguous = acc * scale + bias (flax_qconv.py:158-168 on packed weights). */
+int snnqp_qconv3x3_fwd(const snnqp_block_params *p, const uint8_t *x,
+                       const int8_t *wq, const float *scale, const float *bias,
+                       float *y, void *stream);
+
+/* TCJA attention (models.py:41-95) from the block's un-pooled spikes.
+ *   spikes uint8 [T,B,H,W,C] via p->x_stride_*;  p->Cin = C
+ *   wq_t int8 levels of the (4,T,T) kernel, wq_c of the (4,C,C) kernel, both in
+ *   the reference's own (k,in,out) layout (snnqp_pack_levels)
+ *   scale_t / scale_c: device scalars c / L / (H*W) (snnqp_fold_affine, n=1)
+ *   counts  workspace int32 [B][T][C]
+ *   att     fp32 out, [(t,b)][C] via p->att_stride_* */
+int snnqp_tcja_fwd(const snnqp_block_params *p, const uint8_t *spikes,
+                   const int8_t *wq_t, const int8_t *wq_c, const float *scale_t,
+                   const float *scale_c, int32_t *counts, float *att,
+                   void *stream);
+
+/* 2x2 / stride 2 max-pool of uint8 spikes (models.py:145-147,185-187) for the
+ * blocks whose un-pooled spikes are also needed (TCJA): x [T,B,H,W,C] via
+ * p->x_stride_*, y [T,B,H/2,W/2,C] via p->y_stride_*, C = p->Cin. */
+int snnqp_maxpool2_fwd(const snnqp_block_params *p, const uint8_t *x, uint8_t *y,
+                       void *stream);
+
+/* vote (models.py:253-255): logits[b][g] = mean_j mean_t spikes[t,b,g*group+j]. */
+int snnqp_vote_fwd(const uint8_t *spikes, int T, int B, int N, int group,
+                   int64_t stride_t, int64_t stride_b, float *logits,
+                   void *stream);
+
+/* compute_metrics with mse_loss (train_utils.py:209-225): out[0] += number of
+ * argmax hits, out[1] += sum of squared errors vs one-hot (fp32 atomics). */
+int snnqp_eval_metrics(const float *logits, const int32_t *labels, int B,
+                       int classes, float *out2, void *stream);
+
+/* Number of kernels this library has launched on this thread since the last
+ * call with reset != 0 (bench.py's gpu_launches). */
+int64_t snnqp_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNNQP_H_ */

@@ -1,0 +1,131 @@
+// C-ABI entry points of the fused spiking blocks: argument validation and
+// dispatch between the tcgen05 kernels (umma_conv.cu) and the dp4a kernels
+// (simt.cu).  See include/snnqp.h for the contract.
+#include "common.cuh"
+
+namespace snnqp {
+int launch_conv3x3_simt(const snnqp_block_params &p, const uint8_t *x, const float *att,
+                        const int8_t *wq, const float *scale, const float *bias,
+                        uint8_t *spikes, float *u_final, void *acc_dump, float *y_plain,
+                        cudaStream_t st);
+int launch_dense_simt(const snnqp_block_params &p, int k_pad, const uint8_t *x, const float *att,
+                      const int8_t *wq, const float *scale, const float *bias, uint8_t *spikes,
+                      float *u_final, void *acc_dump, cudaStream_t st);
+int launch_tcja(const snnqp_block_params &p, const uint8_t *spikes, const int8_t *wq_t,
+                const int8_t *wq_c, const float *scale_t, const float *scale_c, int32_t *counts,
+                float *att, cudaStream_t st);
+int launch_maxpool2(const snnqp_block_params &p, const uint8_t *x, uint8_t *y, cudaStream_t st);
+int launch_vote(const uint8_t *s, int T, int B, int N, int group, int64_t stride_t,
+                int64_t stride_b, float *logits, cudaStream_t st);
+int launch_eval_metrics(const float *logits, const int32_t *labels, int B, int classes,
+                        float *out2, cudaStream_t st);
+// umma_conv.cu
+bool umma_conv3x3_supported(const snnqp_block_params &p, const float *att);
+int launch_conv3x3_umma(const snnqp_block_params &p, const uint8_t *x, const int8_t *wq,
+                        const float *scale, const float *bias, uint8_t *spikes, float *u_final,
+                        int32_t *acc_dump, cudaStream_t st);
+
+static int check_conv(const snnqp_block_params *p, const void *x, const void *wq,
+                      const void *scale, const void *bias, const char *fn) {
+  if (!p || !x || !wq || !scale || !bias) return invalid("%s: null pointer", fn);
+  if (p->T <= 0 || p->B <= 0 || p->H <= 0 || p->W <= 0)
+    return invalid("%s: bad shape T=%d B=%d H=%d W=%d", fn, p->T, p->B, p->H, p->W);
+  if ((p->H & 1) || (p->W & 1)) return unsupported("%s: H=%d W=%d must be even", fn, p->H, p->W);
+  if (!(p->Cin == 2 || (p->Cin % 4 == 0 && p->Cin <= 128)))
+    return unsupported("%s: Cin=%d (supported: 2, or a multiple of 4 up to 128)", fn, p->Cin);
+  if (p->Cout % 32 != 0 || p->Cout > 128 || p->Cout <= 0)
+    return unsupported("%s: Cout=%d (supported: multiples of 32 up to 128)", fn, p->Cout);
+  if (!(p->tau > 0.f)) return invalid("%s: tau=%f must be > 0", fn, (double)p->tau);
+  return SNNQP_OK;
+}
+}  // namespace snnqp
+
+using namespace snnqp;
+
+extern "C" {
+
+int snnqp_spiking_conv3x3_fwd(const snnqp_block_params *p, const uint8_t *x, const float *att,
+                              const int8_t *wq, const float *scale, const float *bias,
+                              uint8_t *spikes, float *u_final, void *acc_dump, void *stream) {
+  if (int rc = require_device()) return rc;
+  if (int rc = check_conv(p, x, wq, scale, bias, "snnqp_spiking_conv3x3_fwd")) return rc;
+  if (!spikes) return invalid("snnqp_spiking_conv3x3_fwd: null spikes");
+  if (att && p->Cin == 2) return unsupported("snnqp_spiking_conv3x3_fwd: att with Cin=2");
+  cudaStream_t st = (cudaStream_t)stream;
+  int impl = p->impl;
+  if (impl == SNNQP_IMPL_AUTO)
+    impl = umma_conv3x3_supported(*p, att) ? SNNQP_IMPL_TCGEN05 : SNNQP_IMPL_SIMT;
+  if (impl == SNNQP_IMPL_TCGEN05) {
+    if (!umma_conv3x3_supported(*p, att))
+      return unsupported("snnqp_spiking_conv3x3_fwd: tcgen05 path needs Cin=Cout=128, binary/count input, "
+                         "W in {16,32,64}, pool=1 (got Cin=%d Cout=%d W=%d H=%d pool=%d att=%d)",
+                         p->Cin, p->Cout, p->W, p->H, p->pool, att != nullptr);
+    return launch_conv3x3_umma(*p, x, wq, scale, bias, spikes, u_final, (int32_t *)acc_dump, st);
+  }
+  if (impl != SNNQP_IMPL_SIMT) return invalid("snnqp_spiking_conv3x3_fwd: impl=%d", p->impl);
+  return launch_conv3x3_simt(*p, x, att, wq, scale, bias, spikes, u_final, acc_dump, nullptr, st);
+}
+
+int snnqp_qconv3x3_fwd(const snnqp_block_params *p, const uint8_t *x, const int8_t *wq,
+                       const float *scale, const float *bias, float *y, void *stream) {
+  if (int rc = require_device()) return rc;
+  if (int rc = check_conv(p, x, wq, scale, bias, "snnqp_qconv3x3_fwd")) return rc;
+  if (!y) return invalid("snnqp_qconv3x3_fwd: null output");
+  return launch_conv3x3_simt(*p, x, nullptr, wq, scale, bias, nullptr, nullptr, nullptr, y,
+                             (cudaStream_t)stream);
+}
+
+int snnqp_spiking_dense_fwd(const snnqp_block_params *p, const uint8_t *x, const float *att,
+                            const int8_t *wq, const float *scale, const float *bias,
+                            uint8_t *spikes, float *u_final, void *acc_dump, void *stream) {
+  if (int rc = require_device()) return rc;
+  if (!p || !x || !wq || !scale || !bias || !spikes) return invalid("snnqp_spiking_dense_fwd: null pointer");
+  if (p->T <= 0 || p->B <= 0 || p->Cin <= 0 || p->Cout <= 0)
+    return invalid("snnqp_spiking_dense_fwd: bad shape T=%d B=%d K=%d N=%d", p->T, p->B, p->Cin, p->Cout);
+  if (!(p->tau > 0.f)) return invalid("snnqp_spiking_dense_fwd: tau must be > 0");
+  const int k_pad = (p->Cin + 15) / 16 * 16;
+  if (k_pad > 8192) return unsupported("snnqp_spiking_dense_fwd: K=%d too large (max 8192)", p->Cin);
+  if (att && p->att_mod <= 0) return invalid("snnqp_spiking_dense_fwd: att_mod=%d", p->att_mod);
+  return launch_dense_simt(*p, k_pad, x, att, wq, scale, bias, spikes, u_final, acc_dump,
+                           (cudaStream_t)stream);
+}
+
+int snnqp_tcja_fwd(const snnqp_block_params *p, const uint8_t *spikes, const int8_t *wq_t,
+                   const int8_t *wq_c, const float *scale_t, const float *scale_c,
+                   int32_t *counts, float *att, void *stream) {
+  if (int rc = require_device()) return rc;
+  if (!p || !spikes || !wq_t || !wq_c || !scale_t || !scale_c || !counts || !att)
+    return invalid("snnqp_tcja_fwd: null pointer");
+  if (p->Cin != 128) return unsupported("snnqp_tcja_fwd: C=%d (supported: 128)", p->Cin);
+  if (p->T <= 0 || p->T > 64 || p->B <= 0 || p->H <= 0 || p->W <= 0)
+    return invalid("snnqp_tcja_fwd: bad shape T=%d B=%d H=%d W=%d", p->T, p->B, p->H, p->W);
+  if (p->H * p->W > (1 << 16)) return unsupported("snnqp_tcja_fwd: H*W too large");
+  return launch_tcja(*p, spikes, wq_t, wq_c, scale_t, scale_c, counts, att, (cudaStream_t)stream);
+}
+
+int snnqp_maxpool2_fwd(const snnqp_block_params *p, const uint8_t *x, uint8_t *y, void *stream) {
+  if (int rc = require_device()) return rc;
+  if (!p || !x || !y) return invalid("snnqp_maxpool2_fwd: null pointer");
+  if (p->T <= 0 || p->B <= 0 || p->H <= 0 || p->W <= 0 || (p->H & 1) || (p->W & 1) || p->Cin % 4 != 0)
+    return invalid("snnqp_maxpool2_fwd: bad shape T=%d B=%d H=%d W=%d C=%d", p->T, p->B, p->H, p->W, p->Cin);
+  return launch_maxpool2(*p, x, y, (cudaStream_t)stream);
+}
+
+int snnqp_vote_fwd(const uint8_t *spikes, int T, int B, int N, int group, int64_t stride_t,
+                   int64_t stride_b, float *logits, void *stream) {
+  if (int rc = require_device()) return rc;
+  if (!spikes || !logits) return invalid("snnqp_vote_fwd: null pointer");
+  if (T <= 0 || B <= 0 || N <= 0 || group <= 0 || N % group != 0)
+    return invalid("snnqp_vote_fwd: T=%d B=%d N=%d group=%d", T, B, N, group);
+  return launch_vote(spikes, T, B, N, group, stride_t, stride_b, logits, (cudaStream_t)stream);
+}
+
+int snnqp_eval_metrics(const float *logits, const int32_t *labels, int B, int classes,
+                       float *out2, void *stream) {
+  if (int rc = require_device()) return rc;
+  if (!logits || !labels || !out2 || B <= 0 || classes <= 0)
+    return invalid("snnqp_eval_metrics: bad arguments");
+  return launch_eval_metrics(logits, labels, B, classes, out2, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,62 @@
+"""Build libsnnqp.so (the C-ABI library) in-tree with nvcc for sm_100a.
+
+    python snnquantprune_b200/csrc/build.py [--force]
+
+The .so is git-ignored but travels to the GPU box with the gpurun snapshot."""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+OUT = os.path.join(os.path.dirname(HERE), "libsnnqp.so")
+SOURCES = ["runtime.cu", "pack.cu", "simt.cu", "umma_conv.cu", "api.cu"]
+HEADERS = ["common.cuh", os.path.join(ROOT, "include", "snnqp.h")]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+         "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+
+
+def _stale() -> bool:
+  if not os.path.exists(OUT):
+    return True
+  t = os.path.getmtime(OUT)
+  deps = [os.path.join(HERE, s) for s in SOURCES] + [
+      h if os.path.isabs(h) else os.path.join(HERE, h) for h in HEADERS]
+  deps.append(os.path.abspath(__file__))
+  return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+  if not force and not _stale():
+    return OUT
+  objs = []
+  build_dir = os.path.join(HERE, "build")
+  os.makedirs(build_dir, exist_ok=True)
+  procs = []
+  for s in SOURCES:
+    o = os.path.join(build_dir, s.replace(".cu", ".o"))
+    objs.append(o)
+    cmd = [NVCC, *FLAGS, "-I", os.path.join(ROOT, "include"), "-I", HERE, "-c",
+           os.path.join(HERE, s), "-o", o]
+    procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+  logs = []
+  for s, pr in procs:
+    out, _ = pr.communicate()
+    logs.append(f"==== {s}\n{out}")
+    if pr.returncode != 0:
+      sys.stderr.write("\n".join(logs))
+      raise RuntimeError(f"nvcc failed on {s}")
+  with open(os.path.join(build_dir, "ptxas.log"), "w") as f:
+    f.write("\n".join(logs))
+  if verbose:
+    print("\n".join(logs))
+  cmd = [NVCC, "-shared", "-o", OUT, *objs, "-lcudart"]
+  subprocess.run(cmd, check=True)
+  return OUT
+
+
+if __name__ == "__main__":
+  print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

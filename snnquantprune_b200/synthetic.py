@@ -1,0 +1,128 @@
+"""Synthetic TCJA-SNN parameters and event frames (host-side numpy, no device
+work).
+
+There is no dataset and no checkpoint in this environment (BASELINE.md section
+1), so benchmarks and tests run on random-init weights of the reference
+architecture and synthetic event-count frames:
+
+* kernels ~ N(0, gain^2 / fan_in)  (the layers' default ``lecun_normal`` scale,
+  /root/reference/flax_qconv.py:86, flax_qdense.py:51; ``gain`` > 1 on the
+  BatchNorm-free layers so that they actually fire);
+* DuQ ``a = c = gaussian_init(kernel)``
+  (/root/reference/examples/train_inpt_spikingjelly.py:159-172);
+* ``prune_0/mask`` from global (or local) magnitude pruning (same file,
+  147-223);
+* BatchNorm gamma/beta/mean/var drawn around fixed per-layer constants chosen
+  so that every block fires at a healthy rate (a dead network would make parity
+  checks vacuous);
+* frames: uint8 event counts ``min(Poisson(0.15), 15)``, layout (B,T,H,W,2)
+  (/root/reference/examples/train_inpt_spikingjelly.py:300-305).
+
+The variable tree mirrors the reference's Flax tree (names ``QuantConv_0..8``,
+``QuantDense_0..1``, ``BatchNorm_0..4``;
+/root/reference/examples/tcja/tcja_load_pretrained_weights.py:19-36).
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Dict
+
+import numpy as np
+
+from . import quant as hq
+
+F32 = np.float32
+
+# Gains bring every kernel to a comparable magnitude (std ~0.15-0.3) so that
+# GLOBAL magnitude pruning removes a similar share of every layer instead of
+# wiping out the 3x3x128x128 kernels (whose lecun std is 0.03); BatchNorm makes
+# the conv gains irrelevant to the function, the BN-free layers need > 1 to fire.
+_GAIN = {"QuantConv_1": 7.0, "QuantConv_2": 7.0, "QuantConv_3": 7.0, "QuantConv_6": 7.0,
+         "QuantDense_0": 7.0, "QuantDense_1": 5.0,
+         "QuantConv_4": 3.0, "QuantConv_5": 6.0,
+         "QuantConv_7": 3.0, "QuantConv_8": 6.0}
+# assumed second moment E[x^2] of each conv block's input (counts, then spike
+# rates, then att^2 * rate), used to centre the synthetic running variance
+_IN_M2 = (0.1725, 0.27, 0.36, 0.32, 0.06)
+_CONV_NAMES = ("QuantConv_0", "QuantConv_1", "QuantConv_2", "QuantConv_3", "QuantConv_6")
+
+
+def _effective_energy(kernel, a, mask, bits):
+  """sum_k w_eff[k, n]^2 per output channel of the quantized + masked kernel
+  (synthetic-statistics helper only; the product quantizes on the device)."""
+  L = F32(2 ** (bits - 1) - 1)
+  q = np.round(np.clip(kernel / F32(a), -1, 1) * L) / L * F32(a) * mask
+  return np.sum(q.reshape(-1, q.shape[-1]).astype(np.float64) ** 2, axis=0)
+
+
+def kernel_shapes(T: int, channels: int, num_classes: int, H: int
+                  ) -> "OrderedDict[str, tuple]":
+  """Kernel shapes of CextNet in param-tree order
+  (/root/reference/examples/tcja/models.py:111-246; HWIO / (in,out))."""
+  C = channels
+  side = H // 32
+  return OrderedDict([
+      ("QuantConv_0", (3, 3, 2, C)),
+      ("QuantConv_1", (3, 3, C, C)),
+      ("QuantConv_2", (3, 3, C, C)),
+      ("QuantConv_3", (3, 3, C, C)),
+      ("QuantConv_4", (4, T, T)),       # TCJA-0 conv_t (features = T)
+      ("QuantConv_5", (4, C, C)),       # TCJA-0 conv_c
+      ("QuantConv_6", (3, 3, C, C)),
+      ("QuantConv_7", (4, T, T)),
+      ("QuantConv_8", (4, C, C)),
+      ("QuantDense_0", (C * side * side, C * 2 * 2)),
+      ("QuantDense_1", (C * 2 * 2, num_classes * 10)),
+  ])
+
+
+def make_variables(bits: int = 8, prune_percentage: float = 0.5, T: int = 20,
+                   channels: int = 128, num_classes: int = 11, H: int = 128,
+                   seed: int = 1, prune_global: bool = True) -> Dict:
+  rng = np.random.default_rng(seed)
+  shapes = kernel_shapes(T, channels, num_classes, H)
+  kernels = OrderedDict()
+  for name, shp in shapes.items():
+    fan_in = int(np.prod(shp[:-1]))
+    g = _GAIN.get(name, 1.0)
+    kernels[name] = (rng.standard_normal(shp) * (g / np.sqrt(fan_in))).astype(F32)
+
+  if prune_percentage > 0:
+    if prune_global:
+      masks = hq.global_masks(kernels, prune_percentage)
+    else:
+      masks = OrderedDict((n, hq.local_mask(k, prune_percentage))
+                          for n, k in kernels.items())
+  else:
+    masks = OrderedDict((n, np.ones(k.shape, F32)) for n, k in kernels.items())
+
+  params = OrderedDict()
+  for name, k in kernels.items():
+    ac = hq.gaussian_init(k, bits=bits, sign=True)
+    params[name] = {"kernel": k,
+                    "DuQ_0": {"a": np.array([ac], F32), "c": np.array([ac], F32)},
+                    "prune_0": {"mask": masks[name].astype(F32)}}
+  stats = OrderedDict()
+  for i in range(5):
+    C = channels
+    lay = params[_CONV_NAMES[i]]
+    energy = _effective_energy(lay["kernel"], lay["DuQ_0"]["a"][0], lay["prune_0"]["mask"], bits)
+    var = np.maximum(_IN_M2[i] * energy, 1e-6) * rng.uniform(0.8, 1.25, C)
+    params[f"BatchNorm_{i}"] = {
+        "scale": rng.uniform(0.8, 1.2, C).astype(F32),
+        "bias": (0.5 + 0.1 * rng.standard_normal(C)).astype(F32)}
+    stats[f"BatchNorm_{i}"] = {
+        "mean": (0.05 * np.sqrt(var) * rng.standard_normal(C)).astype(F32),
+        "var": var.astype(F32)}
+  return {"params": params, "batch_stats": stats}
+
+
+def make_frames(B: int, T: int = 20, H: int = 128, W: int = 128, seed: int = 0,
+                rate: float = 0.15) -> np.ndarray:
+  """uint8 event-count frames (B,T,H,W,2)."""
+  rng = np.random.default_rng(seed)
+  return np.minimum(rng.poisson(rate, size=(B, T, H, W, 2)), 15).astype(np.uint8)
+
+
+def make_labels(B: int, num_classes: int = 11, seed: int = 3) -> np.ndarray:
+  return np.random.default_rng(seed).integers(0, num_classes, size=(B,)).astype(np.int32)

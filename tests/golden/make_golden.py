@@ -1,0 +1,98 @@
+"""Generate the committed golden fixtures from the CPU oracle.
+
+    python tests/golden/make_golden.py
+
+The reference itself cannot be imported here (no jax / flax in the image,
+SURVEY.md F2), so these vectors come from the oracle restatements -- the float
+path in the reference's op order (oracle/ref_snn.py) and the integer path
+(oracle/ref_net.py), which must agree before anything is written.  PARITY
+UNPINNED against the real reference; see oracle/__init__.py."""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import ref_int, ref_net, ref_quant, ref_snn  # noqa: E402
+from snnquantprune_b200 import synthetic  # noqa: E402
+
+
+def sha(*arrays) -> str:
+  h = hashlib.sha256()
+  for a in arrays:
+    h.update(np.ascontiguousarray(a).tobytes())
+  return h.hexdigest()
+
+
+def variables_digest(v) -> str:
+  arrs = []
+  for name in sorted(v["params"].keys()):
+    lay = v["params"][name]
+    if "kernel" in lay:
+      arrs += [lay["kernel"], lay["prune_0"]["mask"], lay["DuQ_0"]["a"], lay["DuQ_0"]["c"]]
+    else:
+      arrs += [lay["scale"], lay["bias"], v["batch_stats"][name]["mean"], v["batch_stats"][name]["var"]]
+  return sha(*arrs)
+
+
+def duq_vectors():
+  rng = np.random.default_rng(11)
+  w = np.concatenate([rng.standard_normal(61).astype(np.float32) * 0.3,
+                      np.array([0.0, 1e-9, -1e-9, 0.5, -0.5, 2.0, -2.0], np.float32)])
+  # exact half-way cases for round-half-even at L = 7 and L = 127 with a = 1
+  w = np.concatenate([w, np.array([0.5 / 7, 1.5 / 7, 2.5 / 7, -0.5 / 7, 0.5 / 127, 1.5 / 127], np.float32)])
+  mask = (rng.uniform(size=w.shape) > 0.3).astype(np.float32)
+  out = {"w": w.tolist(), "mask": mask.tolist(), "cases": []}
+  for bits in (2, 4, 8):
+    for a, c in ((1.0, 1.0), (0.37, 0.41)):
+      q = ref_quant.duq_levels(w, a, bits)
+      wq = ref_quant.effective_weight(w, a, c, mask, bits)
+      out["cases"].append({"bits": bits, "a": a, "c": c, "levels": q.tolist(),
+                           "forward": [float(x) for x in wq]})
+  return out
+
+
+def network_fixture(bits, p, T, H, B, seed_w, seed_x):
+  v = synthetic.make_variables(bits=bits, prune_percentage=p, T=T, H=H, seed=seed_w)
+  fr = synthetic.make_frames(B, T, H, H, seed=seed_x)
+  pk = ref_net.pack_network(v, bits, H)
+  ci, cf = {}, {}
+  logits_int = ref_net.forward(pk, fr, collect=ci)
+  logits_f = ref_snn.cextnet_forward(v, fr, bits, collect=cf)
+  # the two restatements must agree before a fixture is written
+  pairs = (("s1", "pool1"), ("s2", "pool2"), ("s3", "pool3"), ("s4", "conv4_spikes"),
+           ("s5", "conv5_spikes"), ("d1", "dense1_spikes"), ("d2", "dense2_spikes"))
+  flips = {a: float(np.mean(ci[a] != (cf[b] != 0))) for a, b in pairs}
+  assert max(flips.values()) <= 1e-4, flips
+  assert np.abs(logits_int - logits_f).max() <= 2e-2
+  fx = {
+      "meta": np.array(json.dumps(dict(bits=bits, prune=p, T=T, H=H, B=B, seed_w=seed_w,
+                                       seed_x=seed_x, variables_sha=variables_digest(v),
+                                       frames_sha=sha(fr), flips_int_vs_float=flips,
+                                       rates=ref_net.firing_rates(ci)))),
+      "logits_int": logits_int, "logits_float": logits_f,
+      "att4": ci["att4"], "att5": ci["att5"],
+      "conv5_u": ci["conv5_u"], "dense2_u": ci["dense2_u"],
+      "conv2_acc_sum": np.array([ci["conv2_acc"].astype(np.int64).sum(),
+                                 (ci["conv2_acc"].astype(np.int64) ** 2).sum()]),
+  }
+  for k in ("s1", "s2", "s3", "s4", "s5", "d1", "d2"):
+    fx[k + "_bits"] = np.packbits(ci[k].reshape(-1))
+    fx[k + "_shape"] = np.array(ci[k].shape)
+  return fx
+
+
+if __name__ == "__main__":
+  with open(os.path.join(HERE, "duq_vectors.json"), "w") as f:
+    json.dump(duq_vectors(), f)
+  np.savez_compressed(os.path.join(HERE, "cextnet_T4_H32_b8_p50.npz"),
+                      **network_fixture(8, 0.5, 4, 32, 2, 1, 0))
+  np.savez_compressed(os.path.join(HERE, "cextnet_T3_H32_b4_p80.npz"),
+                      **network_fixture(4, 0.8, 3, 32, 2, 5, 7))
+  np.savez_compressed(os.path.join(HERE, "cextnet_T3_H32_b2_p90.npz"),
+                      **network_fixture(2, 0.9, 3, 32, 1, 6, 8))
+  print("golden fixtures written")

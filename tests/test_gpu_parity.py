@@ -1,0 +1,509 @@
+"""GPU parity tests (run with -m gpu on a B200): every entry point of the C-ABI
+against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): int32 accumulators, spikes and membranes of
+the integer-input layers bit-exact against the integer-path oracle; membrane
+<= 1e-5 relative and spike flip rate <= 1e-4 where fp32 summation order or expf
+differ (att-weighted layers, whole network vs the fp32 reference-order path)."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_int, ref_net, ref_quant, ref_snn
+from snnquantprune_b200 import _lib, synthetic
+from snnquantprune_b200._lib import BlockParams
+from snnquantprune_b200 import pack as pk_mod
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+F32 = np.float32
+DEV = "cuda"
+
+
+def dev(a, dtype=None):
+  t = torch.as_tensor(np.ascontiguousarray(a), device=DEV)
+  return t if dtype is None else t.to(dtype)
+
+
+def P(t):
+  return _lib.ptr(t)
+
+
+def impls():
+  return [_lib.IMPL_SIMT, _lib.IMPL_TCGEN05]
+
+
+# ------------------------------------------------------------------ pack ----
+@pytest.mark.parametrize("bits", [2, 4, 8])
+def test_pack_kernels_bit_exact(cuda_lib, oracle_lib, bits):
+  rng = np.random.default_rng(bits)
+  k = (rng.standard_normal((3, 3, 128, 128)) * 0.2).astype(F32)
+  mask = ref_quant.local_mask(k, 0.6)
+  a = ref_quant.gaussian_init(k, bits); c = F32(a * 1.1)
+  kd, md = dev(k), dev(mask)
+  ad, cd = dev(np.array([a], F32)), dev(np.array([c], F32))
+  st = _lib.stream()
+  # levels, same layout
+  q = torch.empty(k.shape, device=DEV, dtype=torch.int8)
+  _lib.check(cuda_lib.snnqp_pack_levels(P(kd), P(md), P(ad), bits, k.size, P(q), st))
+  q_ref = ref_int.duq_levels_c(k, mask, a, bits)
+  assert np.array_equal(q.cpu().numpy(), q_ref)
+  assert np.array_equal(q_ref, (ref_quant.duq_levels(k, a, bits) * (mask != 0)).astype(np.int8))
+  # conv3x3 tile layout [9][cout][cin]
+  wq = torch.empty((9, 128, 128), device=DEV, dtype=torch.int8)
+  _lib.check(cuda_lib.snnqp_pack_conv3x3(P(kd), P(md), P(ad), bits, 128, 128, P(wq), st))
+  assert np.array_equal(wq.cpu().numpy(), q_ref.reshape(9, 128, 128).transpose(0, 2, 1))
+  # DuQ + prune forward (fp32)
+  out = torch.empty_like(kd)
+  _lib.check(cuda_lib.snnqp_duq_forward(P(kd), P(md), P(ad), P(cd), bits, k.size, P(out), st))
+  assert np.array_equal(out.cpu().numpy(), ref_quant.effective_weight(k, a, c, mask, bits))
+  # slab bitmap
+  nz = torch.empty((36,), device=DEV, dtype=torch.uint8)
+  _lib.check(cuda_lib.snnqp_conv3x3_slab_bitmap(P(wq), 128, 128, P(nz), st))
+  ref_nz = (q_ref.reshape(9, 4, 32, 128) != 0).any(axis=(2, 3)).reshape(-1)
+  assert np.array_equal(nz.cpu().numpy().astype(bool), ref_nz)
+
+
+def test_pack_matrix_perm_pad_and_golden_vectors(cuda_lib, oracle_lib):
+  rng = np.random.default_rng(9)
+  K, N = 37, 24
+  k = (rng.standard_normal((K, N)) * 0.3).astype(F32)
+  mask = (rng.uniform(size=k.shape) > 0.4).astype(F32)
+  a = ref_quant.max_init(k, 4)
+  perm = rng.permutation(K).astype(np.int32)
+  wq = torch.empty((N, 48), device=DEV, dtype=torch.int8)
+  _lib.check(cuda_lib.snnqp_pack_matrix(P(dev(k)), P(dev(mask)), P(dev(np.array([a], F32))), 4, K, N,
+                                        P(dev(perm)), 48, P(wq), _lib.stream()))
+  q_ref = ref_int.duq_levels_c(k, mask, a, 4)
+  exp = np.zeros((N, 48), np.int8)
+  exp[:, :K] = q_ref[perm].T
+  assert np.array_equal(wq.cpu().numpy(), exp)
+  g = json.load(open(os.path.join(GOLD, "duq_vectors.json")))
+  w = np.array(g["w"], F32); m = np.array(g["mask"], F32)
+  for case in g["cases"]:
+    q = torch.empty(w.shape, device=DEV, dtype=torch.int8)
+    _lib.check(cuda_lib.snnqp_pack_levels(P(dev(w)), None, P(dev(np.array([case["a"]], F32))), case["bits"],
+                                          w.size, P(q), _lib.stream()))
+    assert q.cpu().numpy().astype(np.int32).tolist() == case["levels"]
+    out = torch.empty(w.shape, device=DEV, dtype=torch.float32)
+    _lib.check(cuda_lib.snnqp_duq_forward(P(dev(w)), P(dev(m)), P(dev(np.array([case["a"]], F32))),
+                                          P(dev(np.array([case["c"]], F32))), case["bits"], w.size, P(out),
+                                          _lib.stream()))
+    assert np.array_equal(out.cpu().numpy(), np.array(case["forward"], F32))
+
+
+def test_fold_affine_bit_exact(cuda_lib):
+  rng = np.random.default_rng(10)
+  n = 128
+  bn = dict(scale=rng.uniform(0.5, 1.5, n).astype(F32), bias=rng.standard_normal(n).astype(F32))
+  stt = dict(mean=rng.standard_normal(n).astype(F32), var=rng.uniform(0.01, 2, n).astype(F32))
+  c = np.array([0.731], F32)
+  for bits in (2, 4, 8):
+    s_ref, b_ref = ref_int.fold_affine(c, bits, bn, stt, n)
+    s, b = pk_mod.fold_affine(c, bits, n, DEV, bn, stt)
+    assert np.array_equal(s.cpu().numpy(), s_ref) and np.array_equal(b.cpu().numpy(), b_ref)
+    s_ref, b_ref = ref_int.fold_affine(c, bits, n=1, extra_div=256.0)
+    s, b = pk_mod.fold_affine(c, bits, 1, DEV, extra_div=256.0)
+    assert np.array_equal(s.cpu().numpy(), s_ref) and b.item() == 0.0
+
+
+# ------------------------------------------------------- fused conv block ----
+def run_conv(lib, x_tb, wq, scale, bias, Cout, pool, impl, att=None, tau=2.0, batch_major=False):
+  """x_tb: numpy (T,B,H,W,Cin) u8.  Calls snnqp_spiking_conv3x3_fwd through the
+  C-ABI; returns numpy (spikes (T,B,Ho,Wo,C), u (B,H,W,C), acc (T,B,H,W,C))."""
+  T, B, H, W, Cin = x_tb.shape
+  if batch_major:
+    xs = dev(np.ascontiguousarray(np.swapaxes(x_tb, 0, 1)))
+    xst, xsb = xs.stride(1), xs.stride(0)
+  else:
+    xs = dev(x_tb)
+    xst, xsb = xs.stride(0), xs.stride(1)
+  Ho, Wo = (H // 2, W // 2) if pool else (H, W)
+  spikes = torch.full((T, B, Ho, Wo, Cout), 7, device=DEV, dtype=torch.uint8)
+  u = torch.empty((B, H, W, Cout), device=DEV, dtype=torch.float32)
+  acc = torch.empty((T, B, H, W, Cout), device=DEV, dtype=torch.float32 if att is not None else torch.int32)
+  p = BlockParams()
+  p.T, p.B, p.H, p.W, p.Cin, p.Cout = T, B, H, W, Cin, Cout
+  p.x_stride_t, p.x_stride_b = xst, xsb
+  p.y_stride_t, p.y_stride_b = spikes.stride(0), spikes.stride(1)
+  attd = None
+  if att is not None:
+    attd = dev(att)
+    p.att_stride_t, p.att_stride_b = attd.stride(0), attd.stride(1)
+  p.att_mod = Cin
+  p.tau, p.v_threshold, p.v_reset = tau, 1.0, 0.0
+  p.pool, p.impl = int(pool), impl
+  _lib.check(lib.snnqp_spiking_conv3x3_fwd(p, P(xs), P(attd), P(wq), P(scale), P(bias), P(spikes), P(u),
+                                           P(acc), _lib.stream()))
+  torch.cuda.synchronize()
+  return spikes.cpu().numpy(), u.cpu().numpy(), acc.cpu().numpy()
+
+
+def make_layer(rng, cin, cout, bits, p_prune):
+  k = (rng.standard_normal((3, 3, cin, cout)) * 0.2).astype(F32)
+  mask = ref_quant.local_mask(k, p_prune)
+  a = ref_quant.gaussian_init(k, bits)
+  lay = {"kernel": k, "DuQ_0": {"a": np.array([a], F32), "c": np.array([a], F32)}, "prune_0": {"mask": mask}}
+  q = ref_int.duq_levels_c(k, mask, a, bits)
+  energy = (q.astype(np.float64).reshape(-1, cout) ** 2).sum(0) * (a / (2 ** (bits - 1) - 1)) ** 2
+  bn = dict(scale=rng.uniform(0.8, 1.2, cout).astype(F32), bias=(0.5 + 0.1 * rng.standard_normal(cout)).astype(F32))
+  stt = dict(mean=(0.02 * rng.standard_normal(cout)).astype(F32), var=np.maximum(0.25 * energy, 1e-6).astype(F32))
+  return lay, q, bn, stt
+
+
+@pytest.mark.parametrize("shape,bits,pool", [
+    ((3, 2, 8, 8, 2), 8, True), ((2, 1, 16, 12, 2), 4, False), ((4, 2, 32, 32, 2), 2, True)])
+def test_spiking_conv1_counts_bit_exact(cuda_lib, oracle_lib, shape, bits, pool):
+  T, B, H, W, Cin = shape
+  rng = np.random.default_rng(H * 3 + bits)
+  lay, q, bn, stt = make_layer(rng, 2, 128, bits, 0.3)
+  x = np.minimum(rng.poisson(0.4, size=shape), 255).astype(np.uint8)
+  x[0, 0, 0, 0, :] = 255                                    # maximum count
+  packed = pk_mod.pack_conv3x3(lay, bits, DEV, bn, stt)
+  s_ref, info = ref_int.spiking_conv3x3(x, q, *ref_int.fold_affine(lay["DuQ_0"]["c"], bits, bn, stt, 128),
+                                        pool=pool, want=True)
+  for bm in (False, True):
+    s, u, acc = run_conv(cuda_lib, x, packed.wq, packed.scale, packed.bias, 128, pool, _lib.IMPL_SIMT, batch_major=bm)
+    assert np.array_equal(acc, info["acc"])
+    assert np.array_equal(s, s_ref)
+    assert np.array_equal(u, info["u"])
+  assert 0.02 < s_ref.mean() < 0.9
+
+
+@pytest.mark.parametrize("impl", impls())
+@pytest.mark.parametrize("shape,bits,pool,prune", [
+    ((3, 2, 16, 16, 128), 8, True, 0.5), ((2, 1, 32, 32, 128), 4, True, 0.8),
+    ((2, 2, 64, 64, 128), 8, True, 0.5), ((3, 1, 16, 16, 128), 2, False, 0.9),
+    ((1, 1, 8, 8, 128), 8, False, 0.0)])
+def test_spiking_conv_binary_bit_exact(cuda_lib, oracle_lib, impl, shape, bits, pool, prune):
+  T, B, H, W, Cin = shape
+  p0 = BlockParams(); p0.T, p0.B, p0.H, p0.W, p0.Cin, p0.Cout, p0.pool, p0.impl = T, B, H, W, Cin, 128, int(pool), impl
+  rng = np.random.default_rng(H + bits + T)
+  lay, q, bn, stt = make_layer(rng, 128, 128, bits, prune)
+  x = (rng.uniform(size=shape) < 0.25).astype(np.uint8)
+  packed = pk_mod.pack_conv3x3(lay, bits, DEV, bn, stt)
+  scale, bias = ref_int.fold_affine(lay["DuQ_0"]["c"], bits, bn, stt, 128)
+  s_ref, info = ref_int.spiking_conv3x3(x, q, scale, bias, pool=pool, want=True)
+  try:
+    s, u, acc = run_conv(cuda_lib, x, packed.wq, packed.scale, packed.bias, 128, pool, impl, batch_major=True)
+  except _lib.SnnqpError as e:
+    if impl == _lib.IMPL_TCGEN05 and e.code == 3:
+      pytest.skip("shape outside the tcgen05 kernel's envelope: " + str(e))
+    raise
+  assert np.array_equal(acc, info["acc"]), "int32 accumulators differ"
+  assert np.array_equal(s, s_ref), f"spike flips: {np.mean(s != s_ref)}"
+  assert np.array_equal(u, info["u"]), "membrane differs"
+  assert 0.02 < s_ref.mean() < 0.9
+
+
+def test_spiking_conv_tau_not_power_of_two_and_extremes(cuda_lib, oracle_lib):
+  rng = np.random.default_rng(77)
+  lay, q, bn, stt = make_layer(rng, 128, 128, 8, 0.5)
+  packed = pk_mod.pack_conv3x3(lay, 8, DEV, bn, stt)
+  scale, bias = ref_int.fold_affine(lay["DuQ_0"]["c"], 8, bn, stt, 128)
+  for x in (np.zeros((2, 1, 8, 8, 128), np.uint8), np.ones((2, 1, 8, 8, 128), np.uint8)):
+    s_ref, info = ref_int.spiking_conv3x3(x, q, scale, bias, pool=True, tau=3.0, want=True)
+    s, u, acc = run_conv(cuda_lib, x, packed.wq, packed.scale, packed.bias, 128, True, _lib.IMPL_SIMT, tau=3.0)
+    assert np.array_equal(acc, info["acc"]) and np.array_equal(s, s_ref) and np.array_equal(u, info["u"])
+
+
+def test_spiking_conv_att_within_tolerance(cuda_lib, oracle_lib):
+  """conv5: real-valued input att * spikes; fp32 accumulation order differs from
+  the float64 oracle -> membrane <= 1e-5 relative, flips <= 1e-4."""
+  rng = np.random.default_rng(31)
+  T, B, H = 4, 2, 8
+  lay, q, bn, stt = make_layer(rng, 128, 128, 8, 0.5)
+  x = (rng.uniform(size=(T, B, H, H, 128)) < 0.3).astype(np.uint8)
+  att = rng.uniform(0.05, 1.0, size=(T, B, 128)).astype(F32)
+  packed = pk_mod.pack_conv3x3(lay, 8, DEV, bn, stt)
+  scale, bias = ref_int.fold_affine(lay["DuQ_0"]["c"], 8, bn, stt, 128)
+  accf = ref_int.conv3x3_att_accf(x, att, q)
+  s_ref, u_ref = ref_int.lif_from_acc(accf, scale, bias)
+  s, u, acc = run_conv(cuda_lib, x, packed.wq, packed.scale, packed.bias, 128, False, _lib.IMPL_SIMT, att=att)
+  assert np.max(np.abs(acc - accf) / np.maximum(np.abs(accf), 1.0)) <= 1e-5
+  assert np.mean(s != s_ref) <= 1e-4
+  same = (s == s_ref).all(axis=0)
+  assert np.max((np.abs(u - u_ref) / np.maximum(np.abs(u_ref), 1.0))[same]) <= 1e-5
+  # and given the kernel's own accumulators the epilogue is bit-exact
+  s2, u2 = ref_int.lif_from_acc(acc, scale, bias)
+  assert np.array_equal(s, s2) and np.array_equal(u, u2)
+
+
+def test_qconv_plain_forward(cuda_lib, oracle_lib):
+  from snnquantprune_b200 import QuantConv, QuantConfig
+  rng = np.random.default_rng(41)
+  lay, q, _, _ = make_layer(rng, 128, 128, 8, 0.5)
+  x = (rng.uniform(size=(2, 8, 8, 128)) < 0.3).astype(np.uint8)
+  conv = QuantConv(features=128, kernel_size=(3, 3), padding=((1, 1), (1, 1)), use_bias=False,
+                   config=QuantConfig(bits=8, prune_percentage=0.5), bits=8)
+  y = conv.apply({"params": lay}, dev(x)).cpu().numpy()
+  acc = ref_int.conv3x3_acc(x, q)
+  scale, bias = ref_int.fold_affine(lay["DuQ_0"]["c"], 8, n=128)
+  assert np.array_equal(y, ref_int.fmaf(acc.astype(F32), scale, bias))
+  ref_f = ref_snn.quant_conv(lay, x.astype(F32), 8, ((1, 1), (1, 1)))     # reference op order
+  assert np.max(np.abs(y - ref_f)) <= 1e-5 * max(1.0, np.abs(ref_f).max())
+
+
+# ------------------------------------------------------------ dense / tcja ----
+def run_dense(lib, x, wq, scale, bias, N, att=None, att_mod=0):
+  T, B, K = x.shape
+  xs = dev(x)
+  spikes = torch.empty((T, B, N), device=DEV, dtype=torch.uint8)
+  u = torch.empty((B, N), device=DEV, dtype=torch.float32)
+  acc = torch.empty((T, B, N), device=DEV, dtype=torch.float32 if att is not None else torch.int32)
+  p = BlockParams()
+  p.T, p.B, p.H, p.W, p.Cin, p.Cout = T, B, 1, 1, K, N
+  p.x_stride_t, p.x_stride_b = xs.stride(0), xs.stride(1)
+  p.y_stride_t, p.y_stride_b = spikes.stride(0), spikes.stride(1)
+  attd = None
+  if att is not None:
+    attd = dev(att); p.att_stride_t, p.att_stride_b = attd.stride(0), attd.stride(1)
+  p.att_mod = att_mod
+  p.tau, p.v_threshold, p.v_reset = 2.0, 1.0, 0.0
+  _lib.check(lib.snnqp_spiking_dense_fwd(p, P(xs), P(attd), P(wq), P(scale), P(bias), P(spikes), P(u), P(acc),
+                                         _lib.stream()))
+  torch.cuda.synchronize()
+  return spikes.cpu().numpy(), u.cpu().numpy(), acc.cpu().numpy()
+
+
+@pytest.mark.parametrize("T,B,K,N,bits", [(5, 3, 512, 110, 8), (3, 9, 100, 40, 4), (2, 1, 2048, 512, 2)])
+def test_spiking_dense_binary_bit_exact(cuda_lib, oracle_lib, T, B, K, N, bits):
+  rng = np.random.default_rng(K + N)
+  k = (rng.standard_normal((K, N)) * (5.0 / np.sqrt(K))).astype(F32)
+  mask = ref_quant.local_mask(k, 0.5)
+  a = ref_quant.gaussian_init(k, bits)
+  lay = {"kernel": k, "DuQ_0": {"a": np.array([a], F32), "c": np.array([a], F32)}, "prune_0": {"mask": mask}}
+  packed = pk_mod.pack_dense(lay, bits, DEV)
+  q = ref_int.duq_levels_c(k, mask, a, bits)
+  scale, bias = ref_int.fold_affine(lay["DuQ_0"]["c"], bits, n=N)
+  x = (rng.uniform(size=(T, B, K)) < 0.2).astype(np.uint8)
+  acc_ref = ref_int.dense_acc(x, q)
+  s_ref, u_ref = ref_int.lif_from_acc(acc_ref, scale, bias)
+  s, u, acc = run_dense(cuda_lib, x, packed.wq, packed.scale, packed.bias, N)
+  assert np.array_equal(acc, acc_ref) and np.array_equal(s, s_ref) and np.array_equal(u, u_ref)
+  assert s_ref.mean() > 0.01
+
+
+def test_spiking_dense_att_within_tolerance(cuda_lib, oracle_lib):
+  rng = np.random.default_rng(55)
+  T, B, K, N, Cc = 4, 5, 2048, 512, 128
+  k = (rng.standard_normal((K, N)) * (7.0 / np.sqrt(K))).astype(F32)
+  a = ref_quant.gaussian_init(k, 8)
+  lay = {"kernel": k, "DuQ_0": {"a": np.array([a], F32), "c": np.array([a], F32)},
+         "prune_0": {"mask": ref_quant.local_mask(k, 0.5)}}
+  packed = pk_mod.pack_dense(lay, 8, DEV)
+  q = ref_int.duq_levels_c(k, lay["prune_0"]["mask"], a, 8)
+  scale, bias = ref_int.fold_affine(lay["DuQ_0"]["c"], 8, n=N)
+  x = (rng.uniform(size=(T, B, K)) < 0.15).astype(np.uint8)
+  att = rng.uniform(0.05, 1, size=(T, B, Cc)).astype(F32)
+  att_k = np.tile(att, (1, 1, K // Cc))                       # k % 128 -> channel
+  accf = ref_int.dense_att_accf(x, att_k, q)
+  s_ref, u_ref = ref_int.lif_from_acc(accf, scale, bias)
+  s, u, acc = run_dense(cuda_lib, x, packed.wq, packed.scale, packed.bias, N, att=att, att_mod=Cc)
+  assert np.max(np.abs(acc - accf) / np.maximum(np.abs(accf), 1.0)) <= 1e-5
+  assert np.mean(s != s_ref) <= 1e-4
+  s2, u2 = ref_int.lif_from_acc(acc, scale, bias)
+  assert np.array_equal(s, s2) and np.array_equal(u, u2)
+
+
+def test_tcja_maxpool_vote_metrics(cuda_lib, oracle_lib):
+  rng = np.random.default_rng(61)
+  T, B, H, Cc = 6, 3, 8, 128
+  s = (rng.uniform(size=(T, B, H, H, Cc)) < 0.2).astype(np.uint8)
+  kt = (rng.standard_normal((4, T, T)) * 0.6).astype(F32); kc = (rng.standard_normal((4, Cc, Cc)) * 0.25).astype(F32)
+  lays = []
+  for k in (kt, kc):
+    a = ref_quant.gaussian_init(k, 8)
+    lays.append({"kernel": k, "DuQ_0": {"a": np.array([a], F32), "c": np.array([a], F32)},
+                 "prune_0": {"mask": ref_quant.local_mask(k, 0.3)}})
+  qt = pk_mod.pack_levels(lays[0], 8, DEV); qc = pk_mod.pack_levels(lays[1], 8, DEV)
+  st, _ = pk_mod.fold_affine(lays[0]["DuQ_0"]["c"], 8, 1, DEV, extra_div=float(H * H))
+  sc, _ = pk_mod.fold_affine(lays[1]["DuQ_0"]["c"], 8, 1, DEV, extra_div=float(H * H))
+  sd = dev(s)
+  att = torch.empty((T, B, Cc), device=DEV, dtype=torch.float32)
+  cnt = torch.empty((B, T, Cc), device=DEV, dtype=torch.int32)
+  p = BlockParams(); p.T, p.B, p.H, p.W, p.Cin, p.Cout = T, B, H, H, Cc, Cc
+  p.x_stride_t, p.x_stride_b = sd.stride(0), sd.stride(1)
+  p.att_stride_t, p.att_stride_b = att.stride(0), att.stride(1)
+  _lib.check(cuda_lib.snnqp_tcja_fwd(p, P(sd), P(qt), P(qc), P(st), P(sc), P(cnt), P(att), _lib.stream()))
+  att_ref, info = ref_int.tcja_att(s, qt.cpu().numpy(), st.item(), qc.cpu().numpy(), sc.item(), want=True)
+  assert np.array_equal(cnt.cpu().numpy(), np.transpose(info["cnt"], (1, 0, 2)))
+  got = att.cpu().numpy()
+  assert np.max(np.abs(got - att_ref) / att_ref) <= 2e-6
+  # against the reference-order float path (means, fp32 convs, sigmoid)
+  y_ref, att_f = ref_snn.tcja({"t": lays[0], "c": lays[1]}, ("t", "c"), s.astype(F32), 8, return_att=True)
+  assert np.max(np.abs(got - att_f)) <= 1e-5
+  # maxpool
+  y = torch.empty((T, B, H // 2, H // 2, Cc), device=DEV, dtype=torch.uint8)
+  p.y_stride_t, p.y_stride_b = y.stride(0), y.stride(1)
+  _lib.check(cuda_lib.snnqp_maxpool2_fwd(p, P(sd), P(y), _lib.stream()))
+  assert np.array_equal(y.cpu().numpy(), ref_int.maxpool2_u8(s))
+  # vote + metrics
+  sp = (rng.uniform(size=(T, B, 110)) < 0.25).astype(np.uint8)
+  spd = dev(sp)
+  logits = torch.empty((B, 11), device=DEV, dtype=torch.float32)
+  _lib.check(cuda_lib.snnqp_vote_fwd(P(spd), T, B, 110, 10, spd.stride(0), spd.stride(1), P(logits), _lib.stream()))
+  assert np.array_equal(logits.cpu().numpy(), ref_int.vote(sp))
+  labels = np.array([int(np.argmax(ref_int.vote(sp)[0])), 3, 5], np.int32)
+  out = torch.zeros(2, device=DEV)
+  _lib.check(cuda_lib.snnqp_eval_metrics(P(logits), P(dev(labels)), B, 11, P(out), _lib.stream()))
+  m = ref_snn.eval_metrics(ref_int.vote(sp), labels)
+  assert out[0].item() == float(m["accuracy"].sum())
+  assert np.isclose(out[1].item() / (B * 11), float(m["loss"]), rtol=1e-5)
+
+
+# ------------------------------------------------------------ whole network ----
+def engine_for(v, bits, T, H, impl=_lib.IMPL_AUTO, chunk=16):
+  from snnquantprune_b200 import CextNetEngine, pack_cextnet
+  return CextNetEngine(pack_cextnet(v, bits, T, H, device=DEV), impl=impl, chunk=chunk)
+
+
+@pytest.mark.parametrize("name", ["cextnet_T4_H32_b8_p50", "cextnet_T3_H32_b4_p80", "cextnet_T3_H32_b2_p90"])
+def test_network_against_golden_fixture(cuda_lib, name):
+  z = np.load(os.path.join(GOLD, name + ".npz"))
+  m = json.loads(str(z["meta"]))
+  v = synthetic.make_variables(bits=m["bits"], prune_percentage=m["prune"], T=m["T"], H=m["H"], seed=m["seed_w"])
+  fr = synthetic.make_frames(m["B"], m["T"], m["H"], m["H"], seed=m["seed_x"])
+  import sys
+  sys.path.insert(0, GOLD)
+  import make_golden
+  if make_golden.variables_digest(v) != m["variables_sha"] or make_golden.sha(fr) != m["frames_sha"]:
+    pytest.skip("numpy RNG stream differs from the one the fixture was made with")
+  c = {}
+  logits = engine_for(v, m["bits"], m["T"], m["H"]).forward(dev(fr), collect=c).cpu().numpy()
+  for k in ("s1", "s2", "s3", "s4"):          # integer-input layers: bit-exact
+    got = np.swapaxes(c[k].cpu().numpy(), 0, 1)
+    assert np.array_equal(np.packbits(got.reshape(-1)), z[k + "_bits"]), k
+  assert np.max(np.abs(np.swapaxes(c["att4"].cpu().numpy(), 0, 1) - z["att4"]) / z["att4"]) <= 2e-6
+  for k in ("s5", "d1", "d2"):                # downstream of expf / fp32 sums: flip budget
+    got = np.swapaxes(c[k].cpu().numpy(), 0, 1).reshape(-1)
+    ref = np.unpackbits(z[k + "_bits"])[:got.size]
+    assert np.mean(got != ref) <= 1e-4, k
+  assert np.max(np.abs(logits - z["logits_int"])) <= 1e-2
+  assert np.max(np.abs(logits - z["logits_float"])) <= 1e-2
+
+
+def test_network_layerwise_teacher_forced_and_float_path(cuda_lib, oracle_lib):
+  """Free-running GPU forward; the oracle is fed the GPU's own attention so that
+  every integer-input layer can be compared bit for bit, then the whole thing is
+  compared with the reference-order float path under the north-star tolerances."""
+  bits, p, T, H, B = 8, 0.5, 6, 64, 3
+  v = synthetic.make_variables(bits=bits, prune_percentage=p, T=T, H=H, seed=33)
+  fr = synthetic.make_frames(B, T, H, H, seed=34)
+  c = {}
+  logits = engine_for(v, bits, T, H).forward(dev(fr), collect=c).cpu().numpy()
+  tb = lambda k: np.ascontiguousarray(np.swapaxes(c[k].cpu().numpy(), 0, 1))
+  forced = {"att4": tb("att4"), "s5": tb("s5"), "att5": tb("att5"), "d1": tb("d1")}
+  co = {}
+  lo = ref_net.forward(ref_net.pack_network(v, bits, H), fr, collect=co, forced=forced)
+  for i, k in enumerate(("s1", "s2", "s3", "s4"), 1):
+    assert np.array_equal(tb(k), co[k]), k
+    assert np.array_equal(c[f"conv{i}_acc"].cpu().numpy(), co[f"conv{i}_acc"]), f"conv{i} accumulators"
+    assert np.array_equal(c[f"conv{i}_u"].cpu().numpy(), co[f"conv{i}_u"]), f"conv{i} membrane"
+  assert np.array_equal(tb("p4"), co["p4"])
+  assert np.max(np.abs(tb("att4") - co["att4"]) / co["att4"]) <= 2e-6
+  acc5 = c["conv5_acc"].cpu().numpy()
+  assert np.max(np.abs(acc5 - co["conv5_acc"]) / np.maximum(np.abs(co["conv5_acc"]), 1.0)) <= 1e-5
+  assert np.mean(tb("s5") != co["s5"]) <= 1e-4
+  assert np.array_equal(c["dense2_acc"].cpu().numpy(), co["dense2_acc"])
+  assert np.array_equal(tb("d2"), co["d2"])
+  assert np.array_equal(logits, lo)
+  # reference-order float path, free running
+  cf = {}
+  lf = ref_snn.cextnet_forward(v, fr, bits, collect=cf)
+  for k, kf in (("s1", "pool1"), ("s2", "pool2"), ("s3", "pool3"), ("s4", "conv4_spikes"),
+                ("s5", "conv5_spikes"), ("d1", "dense1_spikes"), ("d2", "dense2_spikes")):
+    assert np.mean(tb(k) != (cf[kf] != 0)) <= 1e-4, k
+  for i in range(1, 6):
+    ug, uf = c[f"conv{i}_u"].cpu().numpy(), cf[f"conv{i}_u"]
+    rel = np.abs(ug - uf) / np.maximum(np.abs(uf), 1.0)
+    assert np.quantile(rel, 0.9999) <= 1e-5, i
+  assert np.max(np.abs(logits - lf)) <= 1e-2
+
+
+def test_full_size_properties(cuda_lib):
+  """BASELINE sizes (H=128, T=20): size-independent properties -- samples are
+  independent (batch permutation equivariance, chunking invariance) and a
+  replayed forward is bit-identical."""
+  bits, T, H, B = 8, 20, 128, 6
+  v = synthetic.make_variables(bits=bits, prune_percentage=0.5, T=T, H=H, seed=1)
+  fr = synthetic.make_frames(B, T, H, H, seed=0)
+  frd = dev(fr)
+  eng = engine_for(v, bits, T, H, chunk=4)
+  l1 = eng.forward(frd).cpu().numpy()
+  l2 = eng.forward(frd).cpu().numpy()
+  assert np.array_equal(l1, l2)
+  perm = np.array([3, 0, 5, 1, 4, 2])
+  lp = eng.forward(dev(fr[perm])).cpu().numpy()
+  assert np.array_equal(lp, l1[perm])
+  l3 = engine_for(v, bits, T, H, chunk=1).forward(frd).cpu().numpy()
+  assert np.array_equal(l3, l1)
+  assert l1.std() > 0 and 0.0 < l1.mean() < 1.0
+
+
+def test_full_size_one_sample_against_oracle(cuda_lib, oracle_lib):
+  """configs[0] geometry (T=20, 128x128), one sample, integer-path oracle."""
+  bits, T, H, B = 8, 20, 128, 1
+  v = synthetic.make_variables(bits=bits, prune_percentage=0.5, T=T, H=H, seed=1)
+  fr = synthetic.make_frames(B, T, H, H, seed=0)
+  c = {}
+  logits = engine_for(v, bits, T, H).forward(dev(fr), collect=c).cpu().numpy()
+  tb = lambda k: np.ascontiguousarray(np.swapaxes(c[k].cpu().numpy(), 0, 1))
+  forced = {"att4": tb("att4"), "s5": tb("s5"), "att5": tb("att5"), "d1": tb("d1")}
+  co = {}
+  lo = ref_net.forward(ref_net.pack_network(v, bits, H), fr, collect=co, forced=forced)
+  for k in ("s1", "s2", "s3", "s4"):
+    assert np.array_equal(tb(k), co[k]), k
+  assert np.array_equal(c["conv2_acc"].cpu().numpy(), co["conv2_acc"])
+  assert np.mean(tb("s5") != co["s5"]) <= 1e-4
+  assert np.array_equal(logits, lo)
+  rates = {k: float(tb(k).mean()) for k in ("s1", "s2", "s3", "s4", "s5", "d1", "d2")}
+  assert min(rates.values()) > 0.01, rates
+
+
+def test_error_behaviour(cuda_lib):
+  p = BlockParams(); p.T, p.B, p.H, p.W, p.Cin, p.Cout = 1, 1, 7, 8, 128, 128
+  p.tau = 2.0
+  d = torch.zeros(16, device=DEV, dtype=torch.uint8)
+  rc = cuda_lib.snnqp_spiking_conv3x3_fwd(p, P(d), None, P(d), P(d), P(d), P(d), None, None, _lib.stream())
+  assert rc == 3 and b"even" in cuda_lib.snnqp_last_error()
+  p.H = 8; p.tau = 0.0
+  rc = cuda_lib.snnqp_spiking_conv3x3_fwd(p, P(d), None, P(d), P(d), P(d), P(d), None, None, _lib.stream())
+  assert rc == 1
+  rc = cuda_lib.snnqp_pack_levels(P(d), None, P(d), 9, 4, P(d), _lib.stream())
+  assert rc == 3
+  rc = cuda_lib.snnqp_vote_fwd(P(d), 2, 1, 11, 10, 11, 22, P(d), _lib.stream())
+  assert rc == 1
+  lay = {"kernel": np.zeros((3, 3, 128, 128), F32), "DuQ_0": {"a": np.array([-1.0], F32), "c": np.array([-1.0], F32)},
+         "prune_0": {"mask": np.ones((3, 3, 128, 128), F32)}}
+  with pytest.raises(NotImplementedError):
+    pk_mod.pack_conv3x3(lay, 8, DEV)
+
+
+def test_spiking_block_facade(cuda_lib, oracle_lib):
+  from snnquantprune_b200 import SpikingBlock, QuantConv, QuantDense, QuantConfig, multi_step_LIF, BatchNorm, atan
+  rng = np.random.default_rng(71)
+  lay, q, bn, stt = make_layer(rng, 128, 128, 8, 0.5)
+  cfg = QuantConfig(bits=8, prune_percentage=0.5)
+  blk = SpikingBlock(connection_fn=QuantConv(features=128, kernel_size=(3, 3), padding=((1, 1), (1, 1)),
+                                             use_bias=False, config=cfg, bits=8),
+                     neural_dynamics=multi_step_LIF(tau=2.0, spike_fn=atan), norm_fn=BatchNorm())
+  x = (rng.uniform(size=(3, 2, 8, 8, 128)) < 0.3).astype(np.uint8)
+  xd = dev(x)
+  carry = SpikingBlock.initialize_carry(xd, blk.connection_fn, blk.norm_fn)
+  assert tuple(carry.shape) == (2, 8, 8, 128) and float(carry.abs().sum()) == 0.0
+  variables = {"params": {"connection_fn": lay, "norm_fn": bn}, "batch_stats": {"norm_fn": stt}}
+  u, s = blk.apply(variables, carry, xd)
+  scale, bias = ref_int.fold_affine(lay["DuQ_0"]["c"], 8, bn, stt, 128)
+  s_ref, info = ref_int.spiking_conv3x3(x, q, scale, bias, pool=False, want=True)
+  assert np.array_equal(s.cpu().numpy(), s_ref) and np.array_equal(u.cpu().numpy(), info["u"])
+  # un-fused LIF step mirrors the reference op order
+  lif = multi_step_LIF(tau=2.0, spike_fn=atan)
+  u0 = torch.zeros(5, device=DEV); xin = torch.tensor([2.0, 1.9999, 0.5, -1.0, 4.0], device=DEV)
+  u1, s1 = lif(u0, xin)
+  ur, sr = ref_snn.lif_step(np.zeros(5, F32), xin.cpu().numpy())
+  assert np.array_equal(u1.cpu().numpy(), ur) and np.array_equal(s1.cpu().numpy(), sr)
