@@ -72,8 +72,13 @@ int snnqp_duq_forward(const float *w, const float *mask, const float *a,
 int snnqp_pack_levels(const float *w, const float *mask, const float *a,
                       int bits, int64_t n, int8_t *q, void *stream);
 
-/* 3x3 HWIO kernel (3,3,cin,cout) -> levels in tile layout [9][cout][cin]
- * (tap-major, one 128-byte K row per output channel when cin == 128). */
+/* 3x3 HWIO kernel (3,3,cin,cout) -> packed weight blob of
+ * snnqp_conv3x3_blob_bytes(cin, cout) bytes: levels in tile layout
+ * [9][cout][cin] (tap-major, one 128-byte K row per output channel when
+ * cin == 128) followed, when cin % 32 == 0, by the 9*cin/32 flags of
+ * snnqp_conv3x3_slab_bitmap (padded to 64 bytes) that drive the block-sparse
+ * skip of all-zero weight K-slabs. */
+int64_t snnqp_conv3x3_blob_bytes(int cin, int cout);
 int snnqp_pack_conv3x3(const float *kernel_hwio, const float *mask,
                        const float *a, int bits, int cin, int cout, int8_t *wq,
                        void *stream);
@@ -122,7 +127,8 @@ typedef struct snnqp_block_params {
  *   x       uint8 [T,B,H,W,Cin] via strides (event counts or {0,1} spikes)
  *   att     NULL, or fp32 per-(t,b,cin) multiplier: input = att * x
  *           (TCJA output y = x_seq * att, models.py:97)
- *   wq      int8 [9][Cout][Cin] (Cin==128) or [Cout][32] (Cin==2, k=tap*2+ci)
+ *   wq      blob from snnqp_pack_conv3x3 (Cin==128) or int8 [Cout][32] from
+ *           snnqp_pack_matrix (Cin==2, k=tap*2+ci)
  *   scale/bias fp32 [Cout] from snnqp_fold_affine
  *   spikes  uint8 [T,B,H',W',Cout] via strides, H' = H/2 if pool else H
  *   u_final NULL or fp32 [B][H][W][Cout]: membrane after the last step

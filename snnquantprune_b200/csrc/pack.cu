@@ -166,7 +166,16 @@ int snnqp_pack_conv3x3(const float *kernel_hwio, const float *mask, const float 
   const int64_t n = 9LL * cin * cout;
   k_pack_conv3x3<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(kernel_hwio, mask, a, bits, cin, cout, wq);
   SNNQP_POST_LAUNCH("k_pack_conv3x3");
+  if (cin % 32 == 0) {   // blob tail: non-zero K-slab bitmap for the block-sparse skip path
+    k_slab_bitmap<<<9 * (cin / 32), 256, 0, (cudaStream_t)stream>>>(wq, cin, cout, reinterpret_cast<uint8_t *>(wq) + n);
+    SNNQP_POST_LAUNCH("k_slab_bitmap");
+  }
   return SNNQP_OK;
+}
+
+int64_t snnqp_conv3x3_blob_bytes(int cin, int cout) {
+  const int64_t n = 9LL * cin * cout;
+  return (cin % 32 == 0) ? n + 64 : n;
 }
 
 int snnqp_pack_matrix(const float *kernel_kn, const float *mask, const float *a, int bits, int K,

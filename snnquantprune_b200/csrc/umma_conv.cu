@@ -1,10 +1,370 @@
-// placeholder until the tcgen05 kernel lands
+// Fused SpikingBlock(QuantConv3x3 -> BN -> LIF [-> 2x2 max-pool]) for binary /
+// count inputs with Cin = Cout = 128, on the 5th-gen tensor cores:
+// tcgen05.mma.kind::i8 fed by TMA, int32 accumulators in TMEM, T loop inside a
+// persistent, warp-specialised kernel.  Reference semantics:
+// SpikingBlock.__call__ spiking_learning.py:441-472 with QuantConv
+// (flax_qconv.py:158-168), eval BatchNorm (examples/tcja/models.py:101-107),
+// multi_step_LIF (spiking_learning.py:404-416) and the pool (models.py:145-147).
+//
+// Mapping ("swapped" implicit GEMM, flat shifts):
+//   D[cout, pos] += sum_{tap, cin} Wq[tap][cout][cin] * X[pos + shift(tap)][cin]
+//   * A operand (M = 128 output channels) = packed weights, resident in shared
+//     memory for the CTA's lifetime: 9 taps x [128 rows x 128 B], 128B swizzle.
+//   * B operand (N = flat output positions) = one TMA box per (strip, timestep):
+//     (TH+2) input rows x (W+2) columns x 128 channels, zero-filled halo (TMA
+//     out-of-bounds fill) -> smem rows of 128 B at pitch P = W+2.  Tap (kh,kw)
+//     is the SAME buffer read from row offset kh*P + kw: the zero columns make
+//     the flat shift exact, so nothing is re-loaded or re-laid-out per tap.
+//   * D (TMEM): lane = output channel, column = flat position r*P + w; the two
+//     pad columns per row hold garbage that is never read.  Two accumulator
+//     buffers so the epilogue of step i overlaps the MMAs of step i+1.
+//   * Epilogue: 8 warps; a thread owns one channel x 64 positions, keeps their
+//     membrane potentials in registers across all T steps, pools 2x2 in-thread.
+#include <mutex>
+
 #include "common.cuh"
+#include "ptx.cuh"
+
 namespace snnqp {
-bool umma_conv3x3_supported(const snnqp_block_params &p, const float *att) { return false; }
-int launch_conv3x3_umma(const snnqp_block_params &p, const uint8_t *x, const int8_t *wq,
-                        const float *scale, const float *bias, uint8_t *spikes, float *u_final,
-                        int32_t *acc_dump, cudaStream_t st) {
-  return unsupported("tcgen05 conv not built");
+
+namespace {
+
+constexpr int kC = 128;
+constexpr int kWBytes = 9 * kC * kC;            // 147456
+constexpr int kTapBytes = kC * kC;              // 16384
+constexpr int kStageBytes = 35840;              // >= (2P+2+N) rows * 128 B for every config, 1024-aligned
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = (kEpiWarps + 2) * 32;  // + TMA warp + MMA warp
+constexpr int kTmemCols = 512;
+constexpr int kAccStride = 256;                 // TMEM column offset of accumulator buffer 1
+constexpr int kSmemBytes = kWBytes + 2 * kStageBytes + 1024 /*barriers*/ + 1024 /*align slack*/;
+
+struct UmmaArgs {
+  int T, B, H, W;
+  int P, N;                  // pitch W+2, MMA N
+  int strips, total_items;
+  int64_t y_stride_t, y_stride_b;
+  float tau, v_th, v_reset;
+  int pool;
+  int base_off_mode;
+  int tb_swapped;            // tensor-map dims 3/4 are (b, t) instead of (t, b)
+  uint32_t stage_tx_bytes;
+  const float *scale, *bias;
+  const uint8_t *slab_nz;    // 36 flags (tap*4 + k32) or nullptr
+  uint8_t *spikes;
+  float *u_final;
+  int32_t *acc_dump;
+};
+
+template <int WCFG> struct Cfg;
+template <> struct Cfg<64> { static constexpr int TH = 2, R = 2, WC = 32; };
+template <> struct Cfg<32> { static constexpr int TH = 4, R = 2, WC = 32; };
+template <> struct Cfg<16> { static constexpr int TH = 8, R = 4, WC = 16; };
+
+template <int WCFG, bool TAU2>
+__global__ void __launch_bounds__(kThreads, 1)
+k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+               const UmmaArgs a) {
+  using CF = Cfg<WCFG>;
+  constexpr int TH = CF::TH, R = CF::R, WC = CF::WC;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t *w_smem = smem;
+  uint8_t *stage_smem = smem + kWBytes;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kWBytes + 2 * kStageBytes);
+  uint64_t *w_full = bars + 0;
+  uint64_t *in_full = bars + 1;     // [2]
+  uint64_t *in_empty = bars + 3;    // [2]
+  uint64_t *acc_full = bars + 5;    // [2]
+  uint64_t *acc_empty = bars + 7;   // [2]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == kEpiWarps && lane == 0) {
+    ptx::prefetch_tmap(&tmap_x);
+    ptx::prefetch_tmap(&tmap_w);
+    ptx::mbar_init(w_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(in_full + i, 1);
+      ptx::mbar_init(in_empty + i, 1);
+      ptx::mbar_init(acc_full + i, 1);
+      ptx::mbar_init(acc_empty + i, kEpiWarps);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == kEpiWarps + 1) ptx::tmem_alloc<kTmemCols>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == kEpiWarps) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      ptx::mbar_expect_tx(w_full, kWBytes);
+      for (int tap = 0; tap < 9; ++tap)
+        ptx::tma_load_2d(w_smem + tap * kTapBytes, &tmap_w, w_full, 0, tap * kC);
+      uint32_t step = 0;
+      for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
+        const int b = item / a.strips, h0 = (item % a.strips) * TH;
+        for (int t = 0; t < a.T; ++t, ++step) {
+          const uint32_t s = step & 1, ph = (step >> 1) & 1;
+          ptx::mbar_wait(in_empty + s, ph ^ 1);
+          ptx::mbar_expect_tx(in_full + s, a.stage_tx_bytes);
+          ptx::tma_load_5d(stage_smem + s * kStageBytes, &tmap_x, in_full + s, 0, -1, h0 - 1,
+                           a.tb_swapped ? b : t, a.tb_swapped ? t : b);
+        }
+      }
+    }
+  } else if (warp == kEpiWarps + 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint64_t nz_mask = ~0ull;
+      if (a.slab_nz) {
+        nz_mask = 0;
+        for (int i = 0; i < 36; ++i) nz_mask |= (uint64_t)(a.slab_nz[i] != 0) << i;
+        if (nz_mask == 0) nz_mask = 1;   // keep one (all-zero) slab so the accumulator is still cleared
+      }
+      const uint32_t idesc = ptx::make_idesc_i8(128, a.N, /*A = weights s8*/ true, /*B = inputs u8*/ false);
+      const uint32_t w_addr = ptx::smem_u32(w_smem);
+      ptx::mbar_wait(w_full, 0);
+      uint32_t step = 0;
+      for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
+        for (int t = 0; t < a.T; ++t, ++step) {
+          const uint32_t s = step & 1, ph = (step >> 1) & 1;
+          ptx::mbar_wait(acc_empty + s, ph ^ 1);
+          ptx::mbar_wait(in_full + s, ph);
+          ptx::tc_fence_after();
+          const uint32_t x_addr = ptx::smem_u32(stage_smem + s * kStageBytes);
+          const uint32_t d_tmem = tmem_base + s * kAccStride;
+          uint32_t accumulate = 0;
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const int kh = tap / 3, kw = tap % 3;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (!((nz_mask >> (tap * 4 + k)) & 1)) continue;     // block-sparse skip of an all-zero K-slab
+              const uint32_t aa = w_addr + tap * kTapBytes + k * 32;
+              const uint32_t ba = x_addr + (kh * a.P + kw) * 128 + k * 32;
+              const uint64_t ad = ptx::make_desc_sw128(aa, 0);
+              const uint64_t bd = ptx::make_desc_sw128(ba, a.base_off_mode ? (ba >> 7) & 7 : 0);
+              ptx::mma_i8(d_tmem, ad, bd, idesc, accumulate);
+              accumulate = 1;
+            }
+          }
+          ptx::mma_commit(in_empty + s);   // input stage reusable once these MMAs have read it
+          ptx::mma_commit(acc_full + s);   // accumulator ready for the epilogue
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue: dequant+BN affine, LIF, pool, store =====================
+    const int q = warp & 3, g = warp >> 2;          // TMEM lane quarter, column group
+    const int c = q * 32 + lane;                    // output channel
+    const float sc = a.scale[c], bi = a.bias[c];
+    const int r0 = (WCFG == 64) ? 0 : g * R;        // first strip row of this thread
+    const int w0 = (WCFG == 64) ? g * WC : 0;       // first column of this thread
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int Wo = a.pool ? a.W / 2 : a.W;
+    float u[R][WC];
+    uint32_t step = 0;
+    for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
+      const int b = item / a.strips, h0 = (item % a.strips) * TH;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int j = 0; j < WC; ++j) u[r][j] = 0.0f;          // zero carry (spiking_learning.py:464-472)
+      for (int t = 0; t < a.T; ++t, ++step) {
+        const uint32_t s = step & 1, ph = (step >> 1) & 1;
+        ptx::mbar_wait(acc_full + s, ph);
+        ptx::tc_fence_after();
+        uint32_t acc[R][WC];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const uint32_t taddr = lane_addr + s * kAccStride + (r0 + r) * a.P + w0;
+          if constexpr (WC == 32) { SNNQP_TMEM_LD_X32(taddr, acc[r]); } else { SNNQP_TMEM_LD_X16(taddr, acc[r]); }
+        }
+        ptx::tc_wait_ld();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(acc_empty + s);        // TMEM buffer free for step + 2
+
+        uint32_t m[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          m[r] = 0;
+#pragma unroll
+          for (int j = 0; j < WC; ++j) {
+            const float v = __fmaf_rn((float)(int32_t)acc[r][j], sc, bi);
+            bool sp;
+            if constexpr (TAU2) {
+              // tau == 2: (x - (u - v_reset)) / 2 == * 0.5 exactly (same rounding as the division)
+              const float un = __fadd_rn(u[r][j], __fmul_rn(__fsub_rn(v, __fsub_rn(u[r][j], a.v_reset)), 0.5f));
+              sp = __fsub_rn(un, a.v_th) >= 0.0f;
+              u[r][j] = sp ? a.v_reset : un;
+            } else {
+              u[r][j] = lif_step(u[r][j], v, a.tau, a.v_th, a.v_reset, sp);
+            }
+            m[r] |= (sp ? 1u : 0u) << j;
+          }
+        }
+        uint8_t *yb = a.spikes + (int64_t)t * a.y_stride_t + (int64_t)b * a.y_stride_b + c;
+        if (a.pool) {
+#pragma unroll
+          for (int pr = 0; pr < R / 2; ++pr) {
+            uint32_t mm = m[2 * pr] | m[2 * pr + 1];
+            mm |= mm >> 1;
+            const int ho = (h0 + r0 + 2 * pr) >> 1;
+#pragma unroll
+            for (int pc = 0; pc < WC / 2; ++pc)
+              yb[((int64_t)ho * Wo + (w0 >> 1) + pc) * kC] = (mm >> (2 * pc)) & 1u;
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int j = 0; j < WC; ++j)
+              yb[((int64_t)(h0 + r0 + r) * Wo + w0 + j) * kC] = (m[r] >> j) & 1u;
+        }
+        if (a.acc_dump) {
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int j = 0; j < WC; ++j)
+              a.acc_dump[((((int64_t)t * a.B + b) * a.H + h0 + r0 + r) * a.W + w0 + j) * kC + c] = (int32_t)acc[r][j];
+        }
+      }
+      if (a.u_final) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int j = 0; j < WC; ++j)
+            a.u_final[(((int64_t)b * a.H + h0 + r0 + r) * a.W + w0 + j) * kC + c] = u[r][j];
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == kEpiWarps + 1) {
+    __syncwarp();
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<kTmemCols>(tmem_base);
+  }
 }
+
+// ---------------------------------------------------------------- host side ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
 }
+
+int th_for(int W) { return W == 64 ? 2 : (W == 32 ? 4 : 8); }
+
+}  // namespace
+
+bool umma_conv3x3_supported(const snnqp_block_params &p, const float *att) {
+  if (att) return false;
+  if (p.Cin != kC || p.Cout != kC) return false;
+  if (!(p.W == 64 || p.W == 32 || p.W == 16)) return false;
+  if (p.H % th_for(p.W) != 0) return false;
+  if (p.x_stride_t % 16 || p.x_stride_b % 16) return false;
+  return true;
+}
+
+int launch_conv3x3_umma(const snnqp_block_params &p, const uint8_t *x, const int8_t *wq, const float *scale,
+                        const float *bias, uint8_t *spikes, float *u_final, int32_t *acc_dump, cudaStream_t st) {
+  EncodeTiledFn encode = get_encode();
+  if (!encode) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return SNNQP_ERR_CUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(wq) & 15))
+    return invalid("tcgen05 conv: x and wq must be 16-byte aligned");
+  const int TH = th_for(p.W), P = p.W + 2;
+  const int nflat = (TH - 1) * P + p.W;
+  const int N = (nflat + 15) / 16 * 16;
+  if ((2 * P + 2 + N) * 128 > kStageBytes) return unsupported("tcgen05 conv: stage buffer too small for W=%d", p.W);
+
+  CUtensorMap tmx, tmw;
+  bool tb_swapped = false;
+  {
+    // a size-1 dimension may carry any stride: give it a sane one
+    const cuuint64_t img = (cuuint64_t)p.H * p.W * kC;
+    cuuint64_t st_t = p.T == 1 ? img : (cuuint64_t)p.x_stride_t;
+    cuuint64_t st_b = p.B == 1 ? img * p.T : (cuuint64_t)p.x_stride_b;
+    tb_swapped = st_t > st_b;          // keep the outer strides non-decreasing
+    cuuint64_t dims[5] = {(cuuint64_t)kC, (cuuint64_t)p.W, (cuuint64_t)p.H,
+                          (cuuint64_t)(tb_swapped ? p.B : p.T), (cuuint64_t)(tb_swapped ? p.T : p.B)};
+    cuuint64_t strides[4] = {(cuuint64_t)kC, (cuuint64_t)p.W * kC, tb_swapped ? st_b : st_t, tb_swapped ? st_t : st_b};
+    cuuint32_t box[5] = {(cuuint32_t)kC, (cuuint32_t)P, (cuuint32_t)(TH + 2), 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&tmx, CU_TENSOR_MAP_DATA_TYPE_UINT8, 5, const_cast<uint8_t *>(x), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(x) failed with CUresult %d (T=%d B=%d H=%d W=%d strides %lld/%lld)", (int)r,
+                p.T, p.B, p.H, p.W, (long long)p.x_stride_t, (long long)p.x_stride_b);
+      return SNNQP_ERR_CUDA;
+    }
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)kC, (cuuint64_t)9 * kC};
+    cuuint64_t strides[1] = {(cuuint64_t)kC};
+    cuuint32_t box[2] = {(cuuint32_t)kC, (cuuint32_t)kC};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&tmw, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t *>(wq), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(w) failed with CUresult %d", (int)r);
+      return SNNQP_ERR_CUDA;
+    }
+  }
+
+  UmmaArgs a;
+  a.T = p.T; a.B = p.B; a.H = p.H; a.W = p.W;
+  a.P = P; a.N = N;
+  a.strips = p.H / TH;
+  a.total_items = p.B * a.strips;
+  a.y_stride_t = p.y_stride_t; a.y_stride_b = p.y_stride_b;
+  a.tau = p.tau; a.v_th = p.v_threshold; a.v_reset = p.v_reset;
+  a.pool = p.pool;
+  a.tb_swapped = tb_swapped ? 1 : 0;
+  const char *bo = getenv("SNNQP_UMMA_BASEOFF");
+  a.base_off_mode = bo ? atoi(bo) : 0;
+  a.stage_tx_bytes = (uint32_t)((TH + 2) * P * kC);
+  a.scale = scale; a.bias = bias;
+  a.slab_nz = reinterpret_cast<const uint8_t *>(wq) + kWBytes;   // blob tail written by snnqp_pack_conv3x3
+  a.spikes = spikes; a.u_final = u_final; a.acc_dump = acc_dump;
+
+  const int grid = a.total_items < sm_count() ? a.total_items : sm_count();
+  const bool tau2 = (p.tau == 2.0f);
+#define SNNQP_LAUNCH_UMMA(WV, T2)                                                                          \
+  do {                                                                                                     \
+    SNNQP_CUDA(cudaFuncSetAttribute(k_conv3x3_umma<WV, T2>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                    kSmemBytes));                                                          \
+    k_conv3x3_umma<WV, T2><<<grid, kThreads, kSmemBytes, st>>>(tmx, tmw, a);                               \
+  } while (0)
+  if (p.W == 64) { if (tau2) SNNQP_LAUNCH_UMMA(64, true); else SNNQP_LAUNCH_UMMA(64, false); }
+  else if (p.W == 32) { if (tau2) SNNQP_LAUNCH_UMMA(32, true); else SNNQP_LAUNCH_UMMA(32, false); }
+  else { if (tau2) SNNQP_LAUNCH_UMMA(16, true); else SNNQP_LAUNCH_UMMA(16, false); }
+#undef SNNQP_LAUNCH_UMMA
+  SNNQP_POST_LAUNCH("k_conv3x3_umma");
+  return SNNQP_OK;
+}
+
+}  // namespace snnqp

@@ -82,13 +82,13 @@ def pack_conv3x3(layer: Mapping[str, Any], bits: int, device, bn=None, stats=Non
                                    None, 32, _lib.ptr(wq), _lib.stream()))
     k_pad = 32
   else:
-    wq = torch.empty((9, cout, cin), device=device, dtype=torch.int8)
+    nbytes = int(L.snnqp_conv3x3_blob_bytes(cin, cout))
+    wq = torch.zeros((nbytes,), device=device, dtype=torch.int8)      # tiles + slab bitmap tail
     _lib.check(L.snnqp_pack_conv3x3(_lib.ptr(kern), _lib.ptr(mask), _lib.ptr(a), bits, cin, cout,
                                     _lib.ptr(wq), _lib.stream()))
     k_pad = cin
     if cin % 32 == 0:
-      slab = torch.empty((9 * (cin // 32),), device=device, dtype=torch.uint8)
-      _lib.check(L.snnqp_conv3x3_slab_bitmap(_lib.ptr(wq), cin, cout, _lib.ptr(slab), _lib.stream()))
+      slab = wq[9 * cin * cout: 9 * cin * cout + 9 * (cin // 32)].view(torch.uint8)
   scale, bias = fold_affine(layer["DuQ_0"]["c"], bits, cout, device, bn, stats)
   return PackedLayer(wq, scale, bias, cin, cout, k_pad, slab)
 

@@ -62,8 +62,11 @@ def test_pack_kernels_bit_exact(cuda_lib, oracle_lib, bits):
   assert np.array_equal(q.cpu().numpy(), q_ref)
   assert np.array_equal(q_ref, (ref_quant.duq_levels(k, a, bits) * (mask != 0)).astype(np.int8))
   # conv3x3 tile layout [9][cout][cin]
-  wq = torch.empty((9, 128, 128), device=DEV, dtype=torch.int8)
-  _lib.check(cuda_lib.snnqp_pack_conv3x3(P(kd), P(md), P(ad), bits, 128, 128, P(wq), st))
+  nb = int(cuda_lib.snnqp_conv3x3_blob_bytes(128, 128))
+  assert nb == 9 * 128 * 128 + 64
+  blob = torch.zeros((nb,), device=DEV, dtype=torch.int8)
+  _lib.check(cuda_lib.snnqp_pack_conv3x3(P(kd), P(md), P(ad), bits, 128, 128, P(blob), st))
+  wq = blob[:9 * 128 * 128].view(9, 128, 128)
   assert np.array_equal(wq.cpu().numpy(), q_ref.reshape(9, 128, 128).transpose(0, 2, 1))
   # DuQ + prune forward (fp32)
   out = torch.empty_like(kd)
@@ -74,6 +77,7 @@ def test_pack_kernels_bit_exact(cuda_lib, oracle_lib, bits):
   _lib.check(cuda_lib.snnqp_conv3x3_slab_bitmap(P(wq), 128, 128, P(nz), st))
   ref_nz = (q_ref.reshape(9, 4, 32, 128) != 0).any(axis=(2, 3)).reshape(-1)
   assert np.array_equal(nz.cpu().numpy().astype(bool), ref_nz)
+  assert np.array_equal(blob[9 * 128 * 128: 9 * 128 * 128 + 36].cpu().numpy().astype(bool), ref_nz)
 
 
 def test_pack_matrix_perm_pad_and_golden_vectors(cuda_lib, oracle_lib):
