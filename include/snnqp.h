@@ -79,6 +79,13 @@ int snnqp_pack_levels(const float *w, const float *mask, const float *a,
  * snnqp_conv3x3_slab_bitmap (padded to 64 bytes) that drive the block-sparse
  * skip of all-zero weight K-slabs. */
 int64_t snnqp_conv3x3_blob_bytes(int cin, int cout);
+
+/* conv1 (cin == 2): blob of snnqp_conv3x3_blob_bytes(2, cout) = 5*cout*32
+ * bytes: [cout][32] with k = tap*2 + ci, then the four quad-position matrices
+ * [4][cout][32] (j = 2*dy + dx, k = py*8 + px*2 + ci over the 4x4x2 input
+ * patch of a 2x2 pool quad) that the tcgen05 conv1 kernel multiplies. */
+int snnqp_pack_conv1(const float *kernel_hwio, const float *mask, const float *a,
+                     int bits, int cout, int8_t *wq, void *stream);
 int snnqp_pack_conv3x3(const float *kernel_hwio, const float *mask,
                        const float *a, int bits, int cin, int cout, int8_t *wq,
                        void *stream);
@@ -127,8 +134,7 @@ typedef struct snnqp_block_params {
  *   x       uint8 [T,B,H,W,Cin] via strides (event counts or {0,1} spikes)
  *   att     NULL, or fp32 per-(t,b,cin) multiplier: input = att * x
  *           (TCJA output y = x_seq * att, models.py:97)
- *   wq      blob from snnqp_pack_conv3x3 (Cin==128) or int8 [Cout][32] from
- *           snnqp_pack_matrix (Cin==2, k=tap*2+ci)
+ *   wq      blob from snnqp_pack_conv3x3 (Cin==128) or snnqp_pack_conv1 (Cin==2)
  *   scale/bias fp32 [Cout] from snnqp_fold_affine
  *   spikes  uint8 [T,B,H',W',Cout] via strides, H' = H/2 if pool else H
  *   u_final NULL or fp32 [B][H][W][Cout]: membrane after the last step

@@ -44,6 +44,7 @@ SIGNATURES = {
     "snnqp_duq_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _vp, _vp]),
     "snnqp_pack_levels": (_i, [_vp, _vp, _vp, _i, _i64, _vp, _vp]),
     "snnqp_conv3x3_blob_bytes": (_i64, [_i, _i]),
+    "snnqp_pack_conv1": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "snnqp_pack_conv3x3": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "snnqp_pack_matrix": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp]),
     "snnqp_fold_affine": (_i, [_vp, _i, _d, _vp, _vp, _vp, _vp, _f, _i, _vp, _vp, _vp]),

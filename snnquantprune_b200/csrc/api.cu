@@ -25,6 +25,11 @@ int launch_conv3x3_umma(const snnqp_block_params &p, const uint8_t *x, const int
                         const float *scale, const float *bias, uint8_t *spikes, float *u_final,
                         int32_t *acc_dump, cudaStream_t st);
 
+// umma_conv1.cu
+bool umma_conv1_supported(const snnqp_block_params &p, const float *att);
+int launch_conv1_umma(const snnqp_block_params &p, const uint8_t *x, const int8_t *wq4, const float *scale,
+                      const float *bias, uint8_t *spikes, float *u_final, int32_t *acc_dump, cudaStream_t st);
+
 static int check_conv(const snnqp_block_params *p, const void *x, const void *wq,
                       const void *scale, const void *bias, const char *fn) {
   if (!p || !x || !wq || !scale || !bias) return invalid("%s: null pointer", fn);
@@ -53,6 +58,18 @@ int snnqp_spiking_conv3x3_fwd(const snnqp_block_params *p, const uint8_t *x, con
   if (att && p->Cin == 2) return unsupported("snnqp_spiking_conv3x3_fwd: att with Cin=2");
   cudaStream_t st = (cudaStream_t)stream;
   int impl = p->impl;
+  if (p->Cin == 2) {
+    // conv1 blob = [Cout][32] tap-major (dp4a-era layout) followed by the 4 quad matrices [4][Cout][32]
+    if (impl == SNNQP_IMPL_AUTO) impl = umma_conv1_supported(*p, att) ? SNNQP_IMPL_TCGEN05 : SNNQP_IMPL_SIMT;
+    if (impl == SNNQP_IMPL_TCGEN05) {
+      if (!umma_conv1_supported(*p, att))
+        return unsupported("snnqp_spiking_conv3x3_fwd: tcgen05 conv1 path needs Cout=128, W %% 64 == 0 (got Cout=%d W=%d)",
+                           p->Cout, p->W);
+      return launch_conv1_umma(*p, x, wq + (int64_t)p->Cout * 32, scale, bias, spikes, u_final, (int32_t *)acc_dump, st);
+    }
+    if (impl != SNNQP_IMPL_SIMT) return invalid("snnqp_spiking_conv3x3_fwd: impl=%d", p->impl);
+    return launch_conv3x3_simt(*p, x, att, wq, scale, bias, spikes, u_final, acc_dump, nullptr, st);
+  }
   if (impl == SNNQP_IMPL_AUTO)
     impl = umma_conv3x3_supported(*p, att) ? SNNQP_IMPL_TCGEN05 : SNNQP_IMPL_SIMT;
   if (impl == SNNQP_IMPL_TCGEN05) {

@@ -84,6 +84,27 @@ __global__ void k_pack_matrix(const float *__restrict__ w, const float *__restri
   }
 }
 
+// conv1 quad-position weight matrices: out[j][o][k], j = 2*dy + dx the output's
+// place in its 2x2 pool quad, k = py*8 + px*2 + ci over the quad's 4x4x2 input
+// patch; the 3x3 window of output (dy,dx) occupies patch pixels (dy+kh, dx+kw).
+__global__ void k_pack_conv1_quad(const float *__restrict__ w, const float *__restrict__ mask,
+                                  const float *__restrict__ a_p, int bits, int cout,
+                                  int8_t *__restrict__ q) {
+  const float a = *a_p;
+  const float L = level_scale(bits);
+  const int64_t n = 4LL * cout * 32;
+  for (int64_t d = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; d < n;
+       d += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(d % 32), o = (int)((d / 32) % cout), j = (int)(d / (32LL * cout));
+    const int py = k >> 3, px = (k >> 1) & 3, ci = k & 1;
+    const int kh = py - (j >> 1), kw = px - (j & 1);
+    int8_t v = 0;
+    if (kh >= 0 && kh < 3 && kw >= 0 && kw < 3)
+      v = level_i8(w, mask, ((int64_t)(kh * 3 + kw) * 2 + ci) * cout + o, a, L);
+    q[d] = v;
+  }
+}
+
 __global__ void k_fold_affine(const float *__restrict__ c_p, int bits, double extra_div,
                               const float *__restrict__ gamma, const float *__restrict__ beta,
                               const float *__restrict__ mean, const float *__restrict__ var,
@@ -173,7 +194,24 @@ int snnqp_pack_conv3x3(const float *kernel_hwio, const float *mask, const float 
   return SNNQP_OK;
 }
 
+int snnqp_pack_conv1(const float *kernel_hwio, const float *mask, const float *a, int bits, int cout,
+                     int8_t *wq, void *stream) {
+  if (int rc = require_device()) return rc;
+  if (!kernel_hwio || !a || !wq) return invalid("snnqp_pack_conv1: null pointer");
+  if (bits < 2 || bits > 8) return unsupported("snnqp_pack_conv1: bits=%d cannot be packed to int8 (need 2..8)", bits);
+  if (cout <= 0) return invalid("snnqp_pack_conv1: cout=%d", cout);
+  // [cout][32], k = tap*2 + ci  (the (3,3,2,cout) kernel seen as an (18, cout) matrix)
+  k_pack_matrix<<<grid_for((int64_t)cout * 32, 256), 256, 0, (cudaStream_t)stream>>>(kernel_hwio, mask, a, bits, 18,
+                                                                                     cout, nullptr, 32, wq);
+  SNNQP_POST_LAUNCH("k_pack_matrix");
+  k_pack_conv1_quad<<<grid_for((int64_t)4 * cout * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      kernel_hwio, mask, a, bits, cout, wq + (int64_t)cout * 32);
+  SNNQP_POST_LAUNCH("k_pack_conv1_quad");
+  return SNNQP_OK;
+}
+
 int64_t snnqp_conv3x3_blob_bytes(int cin, int cout) {
+  if (cin == 2) return 5LL * cout * 32;
   const int64_t n = 9LL * cin * cout;
   return (cin % 32 == 0) ? n + 64 : n;
 }

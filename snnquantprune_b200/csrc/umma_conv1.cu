@@ -1,0 +1,339 @@
+// conv1 of TCJA-SNN on tcgen05: SpikingBlock(QuantConv3x3 (Cin = 2 event-count
+// channels) -> BN -> LIF -> 2x2 max-pool), reference flax_qconv.py:158-168,
+// examples/tcja/models.py:101-147, spiking_learning.py:404-472.
+//
+// K = 3*3*2 = 18 does not fill an int8 MMA K-step (32), so the contraction is
+// restated per 2x2 pool quad: the 4x4x2 input patch that covers a quad is
+// exactly 32 bytes = one K-step, shared by the quad's four outputs through four
+// weight matrices W_j[cout][32] (j = 2*dy + dx; 18 non-zeros each, placed where
+// output (dy,dx)'s 3x3 window sits inside the patch):
+//     D_j[cout, quad] = sum_k W_j[cout][k] * patch[quad][k],  k = py*8 + px*2 + ci
+// One step of one tile = 32 quads (2 output rows x 64 columns) = 4 MMAs of
+// 128 x 32 x 32; the four accumulators of a neuron quad sit in the same TMEM
+// lane, so LIF x4 and the max-pool are thread-local.  The layer is bound by
+// the LIF epilogue (42 M neuron updates per sample), not by the MMAs.
+//
+// Pipeline: TMA (4 input rows x 144 B, zero-filled halo) -> 2 "patch" warps
+// gather the 32-byte K-rows into the canonical no-swizzle K-major layout ->
+// MMA warp -> 8 epilogue warps (membranes in registers across all T steps).
+#include <mutex>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace snnqp {
+
+namespace {
+
+constexpr int kC = 128;
+constexpr int kQuadsPerTile = 32;
+constexpr int kEpiWarps = 8;
+constexpr int kPatchWarps = 2;
+constexpr int kThreads = (kEpiWarps + 2 + kPatchWarps) * 32;   // 384
+// staging stage: 4 input rows x 160 B.  The TMA box must start on a 16-byte boundary in global memory
+// (an inner coordinate of -2 bytes faults with "illegal instruction"), so the box starts 16 bytes left of
+// the tile and the patch warps realign by 14 bytes with byte permutes.
+constexpr int kStRows = 4, kStRowBytes = 160, kStBytes = 640;
+constexpr int kStStages = 4;
+constexpr int kBStages = 2, kBBytes = 4096;                    // 32 quads x 128-byte swizzled rows (32 B used)
+constexpr int kWjBytes = kC * 128;                             // 128 rows x 128-byte swizzled rows (32 B used)
+constexpr int kTmemCols = 256;
+constexpr int kAccStride = 128;                                // 4 x 32 columns per buffer
+
+struct Conv1Args {
+  int T, B, H, W;
+  int tiles_per_row, total_items;
+  int64_t y_stride_t, y_stride_b;
+  float tau, v_th, v_reset;
+  int pool, tb_swapped, debug;
+  const int8_t *wq4;           // [4][cout][32] row-major
+  const float *scale, *bias;
+  uint8_t *spikes;
+  float *u_final;
+  int32_t *acc_dump;
+};
+
+// Operands use the same K-major 128-byte-swizzle layout as the 3x3 kernel: one
+// 128-byte row per M/N index of which only the first 32 bytes (one K-step) are
+// populated; 16-byte chunk c of row r lives at chunk (c ^ (r & 7)).
+__device__ __forceinline__ uint32_t sw128_off(int row, int chunk) {
+  return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
+}
+
+template <bool TAU2>
+__global__ void __launch_bounds__(kThreads, 1)
+k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t *w_smem = smem;                                   // 4 x 16 KB
+  uint8_t *b_smem = smem + 4 * kWjBytes;                    // 2 x 4 KB
+  uint8_t *st_smem = b_smem + kBStages * kBBytes;           // 4 x 640 B
+  uint64_t *bars = reinterpret_cast<uint64_t *>(st_smem + kStStages * kStBytes);
+  uint32_t &tmem_slot = *reinterpret_cast<uint32_t *>(bars + 24);
+  uint64_t *st_full = bars, *st_empty = bars + kStStages;
+  uint64_t *b_full = bars + 2 * kStStages, *b_empty = b_full + kBStages;
+  uint64_t *acc_full = b_empty + kBStages, *acc_empty = acc_full + 2;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // weights: global row-major [4][128][32] -> canonical core-matrix layout
+  for (int i = threadIdx.x; i < 4 * kC * 2; i += kThreads) {
+    const int j = i / (kC * 2), row = (i >> 1) % kC, half = i & 1;
+    const int4 v = *reinterpret_cast<const int4 *>(a.wq4 + ((int64_t)j * kC + row) * 32 + half * 16);
+    *reinterpret_cast<int4 *>(w_smem + j * kWjBytes + sw128_off(row, half)) = v;
+  }
+  ptx::fence_proxy_async();
+  if (warp == kEpiWarps && lane == 0) {
+    ptx::prefetch_tmap(&tmap_x);
+    for (int i = 0; i < kStStages; ++i) { ptx::mbar_init(st_full + i, 1); ptx::mbar_init(st_empty + i, kPatchWarps); }
+    for (int i = 0; i < kBStages; ++i) { ptx::mbar_init(b_full + i, kPatchWarps); ptx::mbar_init(b_empty + i, 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(acc_full + i, 1); ptx::mbar_init(acc_empty + i, kEpiWarps); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == kEpiWarps + 1) ptx::tmem_alloc<kTmemCols>(&tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const int QH = a.H / 2;
+
+  if (warp == kEpiWarps) {
+    // ===================== TMA producer: 4 input rows x 144 B per step =====================
+    if (lane == 0) {
+      uint32_t step = 0;
+      for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
+        const int tile = item % a.tiles_per_row, qh = (item / a.tiles_per_row) % QH;
+        const int b = item / (a.tiles_per_row * QH);
+        for (int t = 0; t < a.T; ++t, ++step) {
+          const uint32_t s = step % kStStages, ph = (step / kStStages) & 1;
+          ptx::mbar_wait(st_empty + s, ph ^ 1);
+          if (a.debug & 2) { ptx::mbar_arrive(st_full + s); continue; }
+          ptx::mbar_expect_tx(st_full + s, kStRows * kStRowBytes);
+          // x coordinate in bytes of the (w, c) axis: patch of quad 0 starts at column 2*qw0 - 1
+          asm volatile(
+              "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+              ::"r"(ptx::smem_u32(st_smem + s * kStBytes)), "l"(reinterpret_cast<uint64_t>(&tmap_x)),
+              "r"(ptx::smem_u32(st_full + s)), "r"(4 * tile * kQuadsPerTile - 16), "r"(2 * qh - 1),
+              "r"(a.tb_swapped ? b : t), "r"(a.tb_swapped ? t : b)
+              : "memory");
+        }
+      }
+    }
+  } else if (warp == kEpiWarps + 1) {
+    // ===================== MMA issuer: 4 x (128 x 32 x 32) per step =====================
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_i8(128, kQuadsPerTile, true, false);
+      const uint32_t w_addr = ptx::smem_u32(w_smem), b_addr = ptx::smem_u32(b_smem);
+      uint32_t step = 0;
+      for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
+        for (int t = 0; t < a.T; ++t, ++step) {
+          const uint32_t s = step & 1, ph = (step >> 1) & 1;
+          ptx::mbar_wait(acc_empty + s, ph ^ 1);
+          ptx::mbar_wait(b_full + s, ph);
+          ptx::tc_fence_after();
+          const uint64_t bd = ptx::make_desc_sw128(b_addr + s * kBBytes, 0);
+          if (!(a.debug & 1)) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              ptx::mma_i8(tmem_base + s * kAccStride + j * kQuadsPerTile,
+                          ptx::make_desc_sw128(w_addr + j * kWjBytes, 0), bd, idesc, 0);
+          }
+          ptx::mma_commit(b_empty + s);
+          ptx::mma_commit(acc_full + s);
+        }
+      }
+    }
+  } else if (warp >= kEpiWarps + 2) {
+    // ===================== patch warps: gather 32-byte K-rows =====================
+    const int pt = threadIdx.x - (kEpiWarps + 2) * 32;     // 0..63
+    const int quad = pt >> 1, half = pt & 1;               // K bytes 16*half .. +15 = patch rows 2*half, 2*half+1
+    uint32_t step = 0;
+    for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
+      for (int t = 0; t < a.T; ++t, ++step) {
+        const uint32_t s = step % kStStages, ph = (step / kStStages) & 1;
+        const uint32_t bs = step & 1, bph = (step >> 1) & 1;
+        ptx::mbar_wait(st_full + s, ph);
+        ptx::mbar_wait(b_empty + bs, bph ^ 1);
+        // patch row bytes sit at offset 14 + 4*quad of the 160-byte staging row: three aligned words, realigned
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(st_smem + s * kStBytes + (2 * half) * kStRowBytes + 12 + 4 * quad);
+        const uint32_t *src2 = reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(src) + kStRowBytes);
+        int4 v;
+        v.x = (int)__byte_perm(src[0], src[1], 0x5432);
+        v.y = (int)__byte_perm(src[1], src[2], 0x5432);
+        v.z = (int)__byte_perm(src2[0], src2[1], 0x5432);
+        v.w = (int)__byte_perm(src2[1], src2[2], 0x5432);
+        *reinterpret_cast<int4 *>(b_smem + bs * kBBytes + sw128_off(quad, half)) = v;
+        ptx::fence_proxy_async();          // generic-proxy writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) {
+          ptx::mbar_arrive(b_full + bs);
+          ptx::mbar_arrive(st_empty + s);
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3, g = warp >> 2;
+    const int c = q * 32 + lane;
+    const float sc = a.scale[c], bi = a.bias[c];
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int Wo = a.pool ? a.W / 2 : a.W;
+    float u[4][16];
+    uint32_t step = 0;
+    for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
+      const int tile = item % a.tiles_per_row, qh = (item / a.tiles_per_row) % QH;
+      const int b = item / (a.tiles_per_row * QH);
+      const int qw0 = tile * kQuadsPerTile + 16 * g;        // first quad column of this thread
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) u[j][i] = 0.0f;
+      for (int t = 0; t < a.T; ++t, ++step) {
+        const uint32_t s = step & 1, ph = (step >> 1) & 1;
+        ptx::mbar_wait(acc_full + s, ph);
+        ptx::tc_fence_after();
+        uint32_t acc[4][16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t taddr = lane_addr + s * kAccStride + j * kQuadsPerTile + 16 * g;
+          SNNQP_TMEM_LD_X16(taddr, acc[j]);
+        }
+        ptx::tc_wait_ld();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(acc_empty + s);
+
+        uint32_t m[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          m[j] = 0;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float v = __fmaf_rn((float)(int32_t)acc[j][i], sc, bi);
+            bool sp;
+            if constexpr (TAU2) {
+              const float un = __fadd_rn(u[j][i], __fmul_rn(__fsub_rn(v, __fsub_rn(u[j][i], a.v_reset)), 0.5f));
+              sp = __fsub_rn(un, a.v_th) >= 0.0f;
+              u[j][i] = sp ? a.v_reset : un;
+            } else {
+              u[j][i] = lif_step(u[j][i], v, a.tau, a.v_th, a.v_reset, sp);
+            }
+            m[j] |= (sp ? 1u : 0u) << i;
+          }
+        }
+        uint8_t *yb = a.spikes + (int64_t)t * a.y_stride_t + (int64_t)b * a.y_stride_b + c;
+        if (a.pool) {
+          const uint32_t mm = m[0] | m[1] | m[2] | m[3];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) yb[((int64_t)qh * Wo + qw0 + i) * kC] = (mm >> i) & 1u;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              yb[((int64_t)(2 * qh + (j >> 1)) * Wo + 2 * (qw0 + i) + (j & 1)) * kC] = (m[j] >> i) & 1u;
+        }
+        if (a.acc_dump) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              a.acc_dump[((((int64_t)t * a.B + b) * a.H + 2 * qh + (j >> 1)) * a.W + 2 * (qw0 + i) + (j & 1)) * kC + c] =
+                  (int32_t)acc[j][i];
+        }
+      }
+      if (a.u_final) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            a.u_final[(((int64_t)b * a.H + 2 * qh + (j >> 1)) * a.W + 2 * (qw0 + i) + (j & 1)) * kC + c] = u[j][i];
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == kEpiWarps + 1) {
+    __syncwarp();
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode1() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+}  // namespace
+
+bool umma_conv1_supported(const snnqp_block_params &p, const float *att) {
+  if (att || p.Cin != 2 || p.Cout != kC) return false;
+  if (p.W % 64 != 0 || (p.H & 1)) return false;
+  if (p.x_stride_t % 16 || p.x_stride_b % 16) return false;
+  return true;
+}
+
+// wq4: [4][128][32] quad-position weight matrices (snnqp_pack_conv1_quad)
+int launch_conv1_umma(const snnqp_block_params &p, const uint8_t *x, const int8_t *wq4, const float *scale,
+                      const float *bias, uint8_t *spikes, float *u_final, int32_t *acc_dump, cudaStream_t st) {
+  EncodeTiledFn encode = get_encode1();
+  if (!encode) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return SNNQP_ERR_CUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(wq4) & 15))
+    return invalid("tcgen05 conv1: x and wq must be 16-byte aligned");
+  CUtensorMap tmx;
+  const cuuint64_t row = (cuuint64_t)p.W * 2, img = row * p.H;
+  cuuint64_t st_t = p.T == 1 ? img : (cuuint64_t)p.x_stride_t;
+  cuuint64_t st_b = p.B == 1 ? img * p.T : (cuuint64_t)p.x_stride_b;
+  const bool swapped = st_t > st_b;
+  cuuint64_t dims[4] = {row, (cuuint64_t)p.H, (cuuint64_t)(swapped ? p.B : p.T), (cuuint64_t)(swapped ? p.T : p.B)};
+  cuuint64_t strides[3] = {row, swapped ? st_b : st_t, swapped ? st_t : st_b};
+  cuuint32_t box[4] = {(cuuint32_t)kStRowBytes, (cuuint32_t)kStRows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = encode(&tmx, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<uint8_t *>(x), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(conv1 x) failed with CUresult %d", (int)r);
+    return SNNQP_ERR_CUDA;
+  }
+  Conv1Args a;
+  a.T = p.T; a.B = p.B; a.H = p.H; a.W = p.W;
+  a.tiles_per_row = (p.W / 2) / kQuadsPerTile;
+  a.total_items = p.B * (p.H / 2) * a.tiles_per_row;
+  a.y_stride_t = p.y_stride_t; a.y_stride_b = p.y_stride_b;
+  a.tau = p.tau; a.v_th = p.v_threshold; a.v_reset = p.v_reset;
+  a.pool = p.pool; a.tb_swapped = swapped ? 1 : 0;
+  const char *dbg = getenv("SNNQP_C1_DEBUG");
+  a.debug = dbg ? atoi(dbg) : 0;
+  a.wq4 = wq4; a.scale = scale; a.bias = bias;
+  a.spikes = spikes; a.u_final = u_final; a.acc_dump = acc_dump;
+  const int grid = a.total_items < sm_count() ? a.total_items : sm_count();
+  constexpr int kSmem = 4 * kWjBytes + kBStages * kBBytes + kStStages * kStBytes + 256 + 1024;
+  if (p.tau == 2.0f) {
+    SNNQP_CUDA(cudaFuncSetAttribute(k_conv1_umma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    k_conv1_umma<true><<<grid, kThreads, kSmem, st>>>(tmx, a);
+  } else {
+    SNNQP_CUDA(cudaFuncSetAttribute(k_conv1_umma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    k_conv1_umma<false><<<grid, kThreads, kSmem, st>>>(tmx, a);
+  }
+  SNNQP_POST_LAUNCH("k_conv1_umma");
+  return SNNQP_OK;
+}
+
+}  // namespace snnqp

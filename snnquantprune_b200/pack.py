@@ -77,9 +77,9 @@ def pack_conv3x3(layer: Mapping[str, Any], bits: int, device, bn=None, stats=Non
   L = _lib.lib()
   slab = None
   if cin == 2:
-    wq = torch.empty((cout, 32), device=device, dtype=torch.int8)
-    _lib.check(L.snnqp_pack_matrix(_lib.ptr(kern), _lib.ptr(mask), _lib.ptr(a), bits, 18, cout,
-                                   None, 32, _lib.ptr(wq), _lib.stream()))
+    wq = torch.zeros((int(L.snnqp_conv3x3_blob_bytes(2, cout)),), device=device, dtype=torch.int8)
+    _lib.check(L.snnqp_pack_conv1(_lib.ptr(kern), _lib.ptr(mask), _lib.ptr(a), bits, cout,
+                                  _lib.ptr(wq), _lib.stream()))
     k_pad = 32
   else:
     nbytes = int(L.snnqp_conv3x3_blob_bytes(cin, cout))

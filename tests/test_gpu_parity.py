@@ -168,6 +168,24 @@ def make_layer(rng, cin, cout, bits, p_prune):
 
 
 @pytest.mark.parametrize("shape,bits,pool", [
+    ((3, 2, 8, 64, 2), 8, True), ((2, 1, 6, 128, 2), 4, False), ((5, 3, 128, 128, 2), 8, True)])
+def test_spiking_conv1_tcgen05_bit_exact(cuda_lib, oracle_lib, shape, bits, pool):
+  T, B, H, W, Cin = shape
+  rng = np.random.default_rng(H * 5 + bits)
+  lay, q, bn, stt = make_layer(rng, 2, 128, bits, 0.3)
+  x = np.minimum(rng.poisson(0.3, size=shape), 255).astype(np.uint8)
+  x[0, 0, 0, 0, :] = 255; x[-1, -1, -1, -1, :] = 200         # extreme counts at the corners
+  packed = pk_mod.pack_conv3x3(lay, bits, DEV, bn, stt)
+  s_ref, info = ref_int.spiking_conv3x3(x, q, *ref_int.fold_affine(lay["DuQ_0"]["c"], bits, bn, stt, 128),
+                                        pool=pool, want=True)
+  for bm in (True, False):
+    s, u, acc = run_conv(cuda_lib, x, packed.wq, packed.scale, packed.bias, 128, pool, _lib.IMPL_TCGEN05, batch_major=bm)
+    assert np.array_equal(acc, info["acc"]), "conv1 int32 accumulators differ"
+    assert np.array_equal(s, s_ref)
+    assert np.array_equal(u, info["u"])
+
+
+@pytest.mark.parametrize("shape,bits,pool", [
     ((3, 2, 8, 8, 2), 8, True), ((2, 1, 16, 12, 2), 4, False), ((4, 2, 32, 32, 2), 2, True)])
 def test_spiking_conv1_counts_bit_exact(cuda_lib, oracle_lib, shape, bits, pool):
   T, B, H, W, Cin = shape
