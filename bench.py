@@ -273,9 +273,10 @@ def dominant_kernel_roofline(eng, frames, args, dev):
   from snnquantprune_b200 import _lib
   L = _lib.lib()
   pk = eng.pk
-  Bc = min(eng.chunk, frames.shape[0])
-  eng._forward_chunk(frames[:Bc], torch.empty((Bc, pk.num_classes), device=dev))
-  ws = eng._workspace(Bc)
+  B = frames.shape[0]
+  Bc = min(eng.chunk, B)
+  eng.forward(frames)
+  ws = eng._workspace(B, Bc)
   lay = pk.convs[1]
   C, Hh = pk.channels, pk.H // 2
   p = eng._bp(Bc, Hh, C, C, ws["s1"], ws["s2"], 1)

@@ -146,6 +146,18 @@ int snnqp_spiking_conv3x3_fwd(const snnqp_block_params *p, const uint8_t *x,
                               uint8_t *spikes, float *u_final, void *acc_dump,
                               void *stream);
 
+/* Same, plus spike_counts (nullable): int32 [B][T][Cout], caller-zeroed;
+ * += the number of UN-pooled spikes of each (b, t, channel) -- the numerator of
+ * the TCJA mean over (h, w) (models.py:42) -- so that the attention can be
+ * computed without materialising the un-pooled spikes (snnqp_tcja_fwd with
+ * spikes == NULL).  On the tcgen05 path att must lie in [0, 1] (it is a
+ * sigmoid): it is evaluated as 24-bit fixed point (three u8 byte planes). */
+int snnqp_spiking_conv3x3_counts_fwd(const snnqp_block_params *p, const uint8_t *x,
+                                     const float *att, const int8_t *wq,
+                                     const float *scale, const float *bias,
+                                     uint8_t *spikes, float *u_final, void *acc_dump,
+                                     int32_t *spike_counts, void *stream);
+
 /* SpikingBlock(QuantDense, multi_step_LIF), no norm (models.py:200-246).
  *   x uint8 [T,B,Cin] via strides; wq int8 [Cout][k_pad] with k_pad = Cin
  *   rounded up to 16; att as above with index k % att_mod. */
@@ -162,7 +174,8 @@ int snnqp_qconv3x3_fwd(const snnqp_block_params *p, const uint8_t *x,
                        float *y, void *stream);
 
 /* TCJA attention (models.py:41-95) from the block's un-pooled spikes.
- *   spikes uint8 [T,B,H,W,C] via p->x_stride_*;  p->Cin = C
+ *   spikes uint8 [T,B,H,W,C] via p->x_stride_*;  p->Cin = C; NULL => counts
+ *          already holds the spike counts (snnqp_spiking_conv3x3_counts_fwd)
  *   wq_t int8 levels of the (4,T,T) kernel, wq_c of the (4,C,C) kernel, both in
  *   the reference's own (k,in,out) layout (snnqp_pack_levels)
  *   scale_t / scale_c: device scalars c / L / (H*W) (snnqp_fold_affine, n=1)

@@ -50,6 +50,7 @@ SIGNATURES = {
     "snnqp_fold_affine": (_i, [_vp, _i, _d, _vp, _vp, _vp, _vp, _f, _i, _vp, _vp, _vp]),
     "snnqp_conv3x3_slab_bitmap": (_i, [_vp, _i, _i, _vp, _vp]),
     "snnqp_spiking_conv3x3_fwd": (_i, [_BP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "snnqp_spiking_conv3x3_counts_fwd": (_i, [_BP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "snnqp_spiking_dense_fwd": (_i, [_BP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "snnqp_qconv3x3_fwd": (_i, [_BP, _vp, _vp, _vp, _vp, _vp, _vp]),
     "snnqp_tcja_fwd": (_i, [_BP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

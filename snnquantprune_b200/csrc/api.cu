@@ -7,7 +7,7 @@ namespace snnqp {
 int launch_conv3x3_simt(const snnqp_block_params &p, const uint8_t *x, const float *att,
                         const int8_t *wq, const float *scale, const float *bias,
                         uint8_t *spikes, float *u_final, void *acc_dump, float *y_plain,
-                        cudaStream_t st);
+                        int32_t *counts, cudaStream_t st);
 int launch_dense_simt(const snnqp_block_params &p, int k_pad, const uint8_t *x, const float *att,
                       const int8_t *wq, const float *scale, const float *bias, uint8_t *spikes,
                       float *u_final, void *acc_dump, cudaStream_t st);
@@ -23,7 +23,16 @@ int launch_eval_metrics(const float *logits, const int32_t *labels, int B, int c
 bool umma_conv3x3_supported(const snnqp_block_params &p, const float *att);
 int launch_conv3x3_umma(const snnqp_block_params &p, const uint8_t *x, const int8_t *wq,
                         const float *scale, const float *bias, uint8_t *spikes, float *u_final,
-                        int32_t *acc_dump, cudaStream_t st);
+                        int32_t *acc_dump, int32_t *counts, cudaStream_t st);
+// umma_att.cu
+bool umma_conv_att_supported(const snnqp_block_params &p, const float *att);
+int launch_conv_att_umma(const snnqp_block_params &p, const uint8_t *x, const float *att, const int8_t *wq,
+                         const float *scale, const float *bias, uint8_t *spikes, float *u_final, float *acc_dump,
+                         int32_t *counts, cudaStream_t st);
+bool umma_dense_supported(const snnqp_block_params &p, const float *att, int k_pad);
+int launch_dense_umma(const snnqp_block_params &p, const uint8_t *x, const float *att, const int8_t *wq,
+                      const float *scale, const float *bias, uint8_t *spikes, float *u_final, void *acc_dump,
+                      cudaStream_t st);
 
 // umma_conv1.cu
 bool umma_conv1_supported(const snnqp_block_params &p, const float *att);
@@ -52,6 +61,13 @@ extern "C" {
 int snnqp_spiking_conv3x3_fwd(const snnqp_block_params *p, const uint8_t *x, const float *att,
                               const int8_t *wq, const float *scale, const float *bias,
                               uint8_t *spikes, float *u_final, void *acc_dump, void *stream) {
+  return snnqp_spiking_conv3x3_counts_fwd(p, x, att, wq, scale, bias, spikes, u_final, acc_dump, nullptr, stream);
+}
+
+int snnqp_spiking_conv3x3_counts_fwd(const snnqp_block_params *p, const uint8_t *x, const float *att,
+                                     const int8_t *wq, const float *scale, const float *bias,
+                                     uint8_t *spikes, float *u_final, void *acc_dump,
+                                     int32_t *spike_counts, void *stream) {
   if (int rc = require_device()) return rc;
   if (int rc = check_conv(p, x, wq, scale, bias, "snnqp_spiking_conv3x3_fwd")) return rc;
   if (!spikes) return invalid("snnqp_spiking_conv3x3_fwd: null spikes");
@@ -61,6 +77,7 @@ int snnqp_spiking_conv3x3_fwd(const snnqp_block_params *p, const uint8_t *x, con
   if (p->Cin == 2) {
     // conv1 blob = [Cout][32] tap-major (dp4a-era layout) followed by the 4 quad matrices [4][Cout][32]
     if (impl == SNNQP_IMPL_AUTO) impl = umma_conv1_supported(*p, att) ? SNNQP_IMPL_TCGEN05 : SNNQP_IMPL_SIMT;
+    if (spike_counts) return unsupported("snnqp_spiking_conv3x3_fwd: spike_counts with Cin=2");
     if (impl == SNNQP_IMPL_TCGEN05) {
       if (!umma_conv1_supported(*p, att))
         return unsupported("snnqp_spiking_conv3x3_fwd: tcgen05 conv1 path needs Cout=128, W %% 64 == 0 (got Cout=%d W=%d)",
@@ -68,7 +85,19 @@ int snnqp_spiking_conv3x3_fwd(const snnqp_block_params *p, const uint8_t *x, con
       return launch_conv1_umma(*p, x, wq + (int64_t)p->Cout * 32, scale, bias, spikes, u_final, (int32_t *)acc_dump, st);
     }
     if (impl != SNNQP_IMPL_SIMT) return invalid("snnqp_spiking_conv3x3_fwd: impl=%d", p->impl);
-    return launch_conv3x3_simt(*p, x, att, wq, scale, bias, spikes, u_final, acc_dump, nullptr, st);
+    return launch_conv3x3_simt(*p, x, att, wq, scale, bias, spikes, u_final, acc_dump, nullptr, nullptr, st);
+  }
+  if (att) {
+    // real-valued input att * x: three byte-plane int8 contractions on tcgen05, or fp32 FMAs (SIMT)
+    if (impl == SNNQP_IMPL_AUTO) impl = umma_conv_att_supported(*p, att) ? SNNQP_IMPL_TCGEN05 : SNNQP_IMPL_SIMT;
+    if (impl == SNNQP_IMPL_TCGEN05) {
+      if (!umma_conv_att_supported(*p, att))
+        return unsupported("snnqp_spiking_conv3x3_fwd: tcgen05 att path needs Cin=Cout=att_mod=128, W=8, H %% 8 == 0 "
+                           "(got Cin=%d Cout=%d W=%d H=%d)", p->Cin, p->Cout, p->W, p->H);
+      return launch_conv_att_umma(*p, x, att, wq, scale, bias, spikes, u_final, (float *)acc_dump, spike_counts, st);
+    }
+    if (impl != SNNQP_IMPL_SIMT) return invalid("snnqp_spiking_conv3x3_fwd: impl=%d", p->impl);
+    return launch_conv3x3_simt(*p, x, att, wq, scale, bias, spikes, u_final, acc_dump, nullptr, spike_counts, st);
   }
   if (impl == SNNQP_IMPL_AUTO)
     impl = umma_conv3x3_supported(*p, att) ? SNNQP_IMPL_TCGEN05 : SNNQP_IMPL_SIMT;
@@ -77,10 +106,10 @@ int snnqp_spiking_conv3x3_fwd(const snnqp_block_params *p, const uint8_t *x, con
       return unsupported("snnqp_spiking_conv3x3_fwd: tcgen05 path needs Cin=Cout=128, binary/count input, "
                          "W in {16,32,64}, pool=1 (got Cin=%d Cout=%d W=%d H=%d pool=%d att=%d)",
                          p->Cin, p->Cout, p->W, p->H, p->pool, att != nullptr);
-    return launch_conv3x3_umma(*p, x, wq, scale, bias, spikes, u_final, (int32_t *)acc_dump, st);
+    return launch_conv3x3_umma(*p, x, wq, scale, bias, spikes, u_final, (int32_t *)acc_dump, spike_counts, st);
   }
   if (impl != SNNQP_IMPL_SIMT) return invalid("snnqp_spiking_conv3x3_fwd: impl=%d", p->impl);
-  return launch_conv3x3_simt(*p, x, att, wq, scale, bias, spikes, u_final, acc_dump, nullptr, st);
+  return launch_conv3x3_simt(*p, x, att, wq, scale, bias, spikes, u_final, acc_dump, nullptr, spike_counts, st);
 }
 
 int snnqp_qconv3x3_fwd(const snnqp_block_params *p, const uint8_t *x, const int8_t *wq,
@@ -88,7 +117,7 @@ int snnqp_qconv3x3_fwd(const snnqp_block_params *p, const uint8_t *x, const int8
   if (int rc = require_device()) return rc;
   if (int rc = check_conv(p, x, wq, scale, bias, "snnqp_qconv3x3_fwd")) return rc;
   if (!y) return invalid("snnqp_qconv3x3_fwd: null output");
-  return launch_conv3x3_simt(*p, x, nullptr, wq, scale, bias, nullptr, nullptr, nullptr, y,
+  return launch_conv3x3_simt(*p, x, nullptr, wq, scale, bias, nullptr, nullptr, nullptr, y, nullptr,
                              (cudaStream_t)stream);
 }
 
@@ -103,6 +132,16 @@ int snnqp_spiking_dense_fwd(const snnqp_block_params *p, const uint8_t *x, const
   const int k_pad = (p->Cin + 15) / 16 * 16;
   if (k_pad > 8192) return unsupported("snnqp_spiking_dense_fwd: K=%d too large (max 8192)", p->Cin);
   if (att && p->att_mod <= 0) return invalid("snnqp_spiking_dense_fwd: att_mod=%d", p->att_mod);
+  int impl = p->impl;
+  if (impl == SNNQP_IMPL_AUTO) impl = umma_dense_supported(*p, att, k_pad) ? SNNQP_IMPL_TCGEN05 : SNNQP_IMPL_SIMT;
+  if (impl == SNNQP_IMPL_TCGEN05) {
+    if (!umma_dense_supported(*p, att, k_pad))
+      return unsupported("snnqp_spiking_dense_fwd: tcgen05 path needs K %% 128 == 0, rows (b,t) contiguous, "
+                         "att_mod=128 (got K=%d T=%d x_stride_t=%lld x_stride_b=%lld)", p->Cin, p->T,
+                         (long long)p->x_stride_t, (long long)p->x_stride_b);
+    return launch_dense_umma(*p, x, att, wq, scale, bias, spikes, u_final, acc_dump, (cudaStream_t)stream);
+  }
+  if (impl != SNNQP_IMPL_SIMT) return invalid("snnqp_spiking_dense_fwd: impl=%d", p->impl);
   return launch_dense_simt(*p, k_pad, x, att, wq, scale, bias, spikes, u_final, acc_dump,
                            (cudaStream_t)stream);
 }
@@ -111,7 +150,7 @@ int snnqp_tcja_fwd(const snnqp_block_params *p, const uint8_t *spikes, const int
                    const int8_t *wq_c, const float *scale_t, const float *scale_c,
                    int32_t *counts, float *att, void *stream) {
   if (int rc = require_device()) return rc;
-  if (!p || !spikes || !wq_t || !wq_c || !scale_t || !scale_c || !counts || !att)
+  if (!p || !wq_t || !wq_c || !scale_t || !scale_c || !counts || !att)
     return invalid("snnqp_tcja_fwd: null pointer");
   if (p->Cin != 128) return unsupported("snnqp_tcja_fwd: C=%d (supported: 128)", p->Cin);
   if (p->T <= 0 || p->T > 64 || p->B <= 0 || p->H <= 0 || p->W <= 0)

@@ -151,5 +151,28 @@ __host__ __device__ constexpr uint32_t make_idesc_i8(int M, int N, bool a_signed
       : "r"(taddr)                                                                                      \
       : "memory")
 
+#define SNNQP_TMEM_LD_X8(taddr, r)                                                                      \
+  asm volatile(                                                                                         \
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"                   \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) \
+      : "r"(taddr)                                                                                      \
+      : "memory")
+
+// named barrier among a subset of warps (id 1..15; id 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// 24-bit fixed point of an attention value in [0, 1]: round(att * 2^24), saturated
+__device__ __forceinline__ uint32_t att_fix24(float att) {
+  const uint32_t f = __float2uint_rn(__fmul_rn(att, 16777216.0f));
+  return f > 0xFFFFFFu ? 0xFFFFFFu : f;
+}
+// recombine the three byte-plane accumulators: (a2 * 2^16 + a1 * 2^8 + a0) * 2^-24
+__device__ __forceinline__ float att_combine(int32_t a2, int32_t a1, int32_t a0) {
+  const float f = __fmaf_rn((float)a2, 65536.0f, __fmaf_rn((float)a1, 256.0f, (float)a0));
+  return __fmul_rn(f, 5.9604644775390625e-8f);
+}
+
 }  // namespace ptx
 }  // namespace snnqp

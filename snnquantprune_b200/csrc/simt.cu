@@ -23,7 +23,7 @@ k_conv3x3_simt(const snnqp_block_params p, const uint8_t *__restrict__ x,
                const float *__restrict__ att, const int8_t *__restrict__ wq,
                const float *__restrict__ scale, const float *__restrict__ bias,
                uint8_t *__restrict__ spikes, float *__restrict__ u_final,
-               void *__restrict__ acc_dump, float *__restrict__ y_plain) {
+               void *__restrict__ acc_dump, float *__restrict__ y_plain, int32_t *__restrict__ counts) {
   extern __shared__ uint32_t sw[];   // [9][C4][Cout]
   const int Cin = p.Cin, Cout = p.Cout, C4 = Cin / 4;
   const uint32_t *wq32 = reinterpret_cast<const uint32_t *>(wq);
@@ -94,6 +94,7 @@ k_conv3x3_simt(const snnqp_block_params p, const uint8_t *__restrict__ x,
       }
       // epilogue: folded dequant+BN affine, then LIF / plain store
       bool any = false;
+      int nspk = 0;
 #pragma unroll
       for (int pos = 0; pos < 4; ++pos) {
         const int oh = 2 * qh + (pos >> 1), ow = 2 * qw + (pos & 1);
@@ -111,11 +112,13 @@ k_conv3x3_simt(const snnqp_block_params p, const uint8_t *__restrict__ x,
         bool s;
         u[pos] = lif_step(u[pos], v, p.tau, p.v_threshold, p.v_reset, s);
         any |= s;
+        nspk += s ? 1 : 0;
         if (!p.pool)
           spikes[(int64_t)t * p.y_stride_t + (int64_t)b * p.y_stride_b + ((int64_t)oh * Wo + ow) * Cout + o] = s ? 1 : 0;
       }
       if (MODE == 0 && p.pool)
         spikes[(int64_t)t * p.y_stride_t + (int64_t)b * p.y_stride_b + ((int64_t)qh * Wo + qw) * Cout + o] = any ? 1 : 0;
+      if (MODE == 0 && counts && nspk) atomicAdd(counts + ((int64_t)b * p.T + t) * Cout + o, nspk);
     }
     if (MODE == 0 && u_final) {
 #pragma unroll
@@ -334,7 +337,7 @@ k_tcja_counts(const snnqp_block_params p, const uint8_t *__restrict__ s,
     counts[((int64_t)b * p.T + t) * C + i] = red[i];
 }
 
-// one block per sample: att[t,b,c] = sigmoid(c_out[t,b,c] * t_out[t,b,c])
+// att[t,b,c] = sigmoid(c_out[t,b,c] * t_out[t,b,c])
 //   t_out[t',b,c] = scale_t * sum_{j<4, t} cnt[t][c+j-1] * q_t[j][t][t']   (conv over the channel axis, features = T)
 //   c_out[t,b,c'] = scale_c * sum_{j<4, c} cnt[t+j-1][c] * q_c[j][c][c']   (conv over the time axis, features = C)
 // 'SAME' pads for k=4: low 1, high 2 (reference flax_qconv.py:131-142).
@@ -343,30 +346,32 @@ k_tcja_att(const snnqp_block_params p, const int32_t *__restrict__ counts,
            const int8_t *__restrict__ wq_t, const int8_t *__restrict__ wq_c,
            const float *__restrict__ scale_t, const float *__restrict__ scale_c,
            float *__restrict__ att) {
+  // one block per (t, b), one thread per channel; the sample's counts are staged in smem
   extern __shared__ int32_t cnt[];   // [T][C]
-  const int b = blockIdx.x, T = p.T, C = p.Cin;
+  const int t = blockIdx.x, b = blockIdx.y, T = p.T, C = p.Cin;
   for (int d = threadIdx.x; d < T * C; d += blockDim.x) cnt[d] = counts[(int64_t)b * T * C + d];
   __syncthreads();
   const float st = *scale_t, scc = *scale_c;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    for (int t = 0; t < T; ++t) {
-      int acc_t = 0, acc_c = 0;
-      for (int j = 0; j < 4; ++j) {
-        const int cc = c + j - 1;
-        if (cc >= 0 && cc < C)
-          for (int ti = 0; ti < T; ++ti)
-            acc_t += cnt[ti * C + cc] * (int)wq_t[(j * T + ti) * T + t];
-        const int tt = t + j - 1;
-        if (tt >= 0 && tt < T)
-          for (int ci = 0; ci < C; ++ci)
-            acc_c += cnt[tt * C + ci] * (int)wq_c[((int64_t)j * C + ci) * C + c];
+    int acc_t = 0, acc_c = 0;
+    for (int j = 0; j < 4; ++j) {
+      const int cc = c + j - 1;
+      if (cc >= 0 && cc < C)
+        for (int ti = 0; ti < T; ++ti)
+          acc_t += cnt[ti * C + cc] * (int)__ldg(wq_t + (j * T + ti) * T + t);          // warp-uniform weight
+      const int tt = t + j - 1;
+      if (tt >= 0 && tt < T) {
+        const int32_t *row = cnt + tt * C;
+        const int8_t *wc = wq_c + (int64_t)j * C * C + c;                              // coalesced over c
+#pragma unroll 8
+        for (int ci = 0; ci < C; ++ci) acc_c += row[ci] * (int)__ldg(wc + (int64_t)ci * C);
       }
-      const float to = __fmul_rn((float)acc_t, st);
-      const float co = __fmul_rn((float)acc_c, scc);
-      const float pr = __fmul_rn(co, to);
-      const float a = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-pr)));
-      att[(int64_t)t * p.att_stride_t + (int64_t)b * p.att_stride_b + c] = a;
     }
+    const float to = __fmul_rn((float)acc_t, st);
+    const float co = __fmul_rn((float)acc_c, scc);
+    const float pr = __fmul_rn(co, to);
+    const float a = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-pr)));
+    att[(int64_t)t * p.att_stride_t + (int64_t)b * p.att_stride_b + c] = a;
   }
 }
 
@@ -439,7 +444,7 @@ __global__ void k_eval_metrics(const float *__restrict__ logits, const int32_t *
 int launch_conv3x3_simt(const snnqp_block_params &p, const uint8_t *x, const float *att,
                         const int8_t *wq, const float *scale, const float *bias,
                         uint8_t *spikes, float *u_final, void *acc_dump, float *y_plain,
-                        cudaStream_t st) {
+                        int32_t *counts, cudaStream_t st) {
   const int64_t quads = (int64_t)p.B * (p.H / 2) * (p.W / 2);
   if (p.Cin == 2) {
     const int block = 256;
@@ -464,7 +469,7 @@ int launch_conv3x3_simt(const snnqp_block_params &p, const uint8_t *x, const flo
     SNNQP_CUDA(cudaFuncSetAttribute(k_conv3x3_simt<ATTV, MODEV>,                              \
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     k_conv3x3_simt<ATTV, MODEV><<<(int)g, block, smem, st>>>(p, x, att, wq, scale, bias,      \
-                                                            spikes, u_final, acc_dump, y_plain); \
+                                                            spikes, u_final, acc_dump, y_plain, counts); \
   } while (0)
   if (y_plain) {
     if (att) SNNQP_LAUNCH_CONV(true, 1); else SNNQP_LAUNCH_CONV(false, 1);
@@ -495,10 +500,12 @@ int launch_dense_simt(const snnqp_block_params &p, int k_pad, const uint8_t *x, 
 int launch_tcja(const snnqp_block_params &p, const uint8_t *spikes, const int8_t *wq_t,
                 const int8_t *wq_c, const float *scale_t, const float *scale_c, int32_t *counts,
                 float *att, cudaStream_t st) {
-  k_tcja_counts<<<p.T * p.B, 256, 0, st>>>(p, spikes, counts);
-  SNNQP_POST_LAUNCH("k_tcja_counts");
+  if (spikes) {   // else: counts were accumulated by the producing conv block (spike_counts output)
+    k_tcja_counts<<<p.T * p.B, 256, 0, st>>>(p, spikes, counts);
+    SNNQP_POST_LAUNCH("k_tcja_counts");
+  }
   const size_t smem = (size_t)p.T * p.Cin * sizeof(int32_t);
-  k_tcja_att<<<p.B, 128, smem, st>>>(p, counts, wq_t, wq_c, scale_t, scale_c, att);
+  k_tcja_att<<<dim3(p.T, p.B), 128, smem, st>>>(p, counts, wq_t, wq_c, scale_t, scale_c, att);
   SNNQP_POST_LAUNCH("k_tcja_att");
   return SNNQP_OK;
 }

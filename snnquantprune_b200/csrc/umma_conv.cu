@@ -54,6 +54,7 @@ struct UmmaArgs {
   uint8_t *spikes;
   float *u_final;
   int32_t *acc_dump;
+  int32_t *counts;           // [B][T][C] += un-pooled spike count (nullable)
 };
 
 template <int WCFG> struct Cfg;
@@ -209,6 +210,12 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             m[r] |= (sp ? 1u : 0u) << j;
           }
         }
+        if (a.counts) {
+          int nspk = 0;
+#pragma unroll
+          for (int r = 0; r < R; ++r) nspk += __popc(m[r]);
+          if (nspk) atomicAdd(a.counts + ((int64_t)b * a.T + t) * kC + c, nspk);
+        }
         uint8_t *yb = a.spikes + (int64_t)t * a.y_stride_t + (int64_t)b * a.y_stride_b + c;
         if (a.pool) {
 #pragma unroll
@@ -286,7 +293,8 @@ bool umma_conv3x3_supported(const snnqp_block_params &p, const float *att) {
 }
 
 int launch_conv3x3_umma(const snnqp_block_params &p, const uint8_t *x, const int8_t *wq, const float *scale,
-                        const float *bias, uint8_t *spikes, float *u_final, int32_t *acc_dump, cudaStream_t st) {
+                        const float *bias, uint8_t *spikes, float *u_final, int32_t *acc_dump, int32_t *counts,
+                        cudaStream_t st) {
   EncodeTiledFn encode = get_encode();
   if (!encode) {
     set_error("cuTensorMapEncodeTiled not available from the driver");
@@ -349,7 +357,7 @@ int launch_conv3x3_umma(const snnqp_block_params &p, const uint8_t *x, const int
   a.stage_tx_bytes = (uint32_t)((TH + 2) * P * kC);
   a.scale = scale; a.bias = bias;
   a.slab_nz = reinterpret_cast<const uint8_t *>(wq) + kWBytes;   // blob tail written by snnqp_pack_conv3x3
-  a.spikes = spikes; a.u_final = u_final; a.acc_dump = acc_dump;
+  a.spikes = spikes; a.u_final = u_final; a.acc_dump = acc_dump; a.counts = counts;
 
   const int grid = a.total_items < sm_count() ? a.total_items : sm_count();
   const bool tau2 = (p.tau == 2.0f);

@@ -2,15 +2,20 @@
 path = the sequence of fused C-ABI calls below, all on the caller's stream.
 
 Graph (reference examples/tcja/models.py:101-257, eval branch):
-  3 x [QuantConv3x3 -> BN -> LIF -> maxpool2]            fused per block
-  2 x [QuantConv3x3 -> BN -> LIF -> TCJA -> maxpool2]    conv block, pool, TCJA attention
+  3 x [QuantConv3x3 -> BN -> LIF -> maxpool2]            one fused launch per block
+  2 x [QuantConv3x3 -> BN -> LIF -> TCJA -> maxpool2]    fused conv block (pooled spikes + per-(b,t,c)
+                                                         spike counts), then the attention kernel
   flatten (folded into dense1 weights) -> [QuantDense -> LIF] x 2 -> vote
 
 Activations stay on the device as uint8 spikes, batch-major [B][T][H][W][C]
 (the reference's input layout, examples/train_inpt_spikingjelly.py:300-305), so
 a batch shard is one contiguous slab.  The TCJA output ``x_seq * att`` is never
-materialised: since att > 0 is constant over (h, w), maxpool(att * s) =
-att * maxpool(s), so consumers take the (pooled spikes, att) pair.
+materialised: att > 0 is constant over (h, w), so maxpool(att * s) =
+att * maxpool(s) and the consumers take the (pooled spikes, att) pair; the TCJA
+mean over (h, w) only needs the spike counts, which the conv epilogue
+accumulates.  The first three blocks run per ``chunk`` samples (their
+activations then stay L2-resident between launches); the small tail layers run
+once over the whole batch so that they fill the machine.
 """
 from __future__ import annotations
 
@@ -32,37 +37,39 @@ class CextNetEngine:
     self.tau, self.v_th, self.v_reset = tau, v_threshold, v_reset
     self.chunk = chunk
     self.device = torch.device(device)
-    self._ws: Dict[int, Dict[str, torch.Tensor]] = {}
+    self._ws: Dict[tuple, Dict[str, torch.Tensor]] = {}
+    self._graphs: Dict[tuple, tuple] = {}
 
   # -- workspace -------------------------------------------------------------
-  def _workspace(self, Bc: int) -> Dict[str, torch.Tensor]:
-    ws = self._ws.get(Bc)
+  def _workspace(self, B: int, Bc: int) -> Dict[str, torch.Tensor]:
+    key = (B, Bc)
+    ws = self._ws.get(key)
     if ws is not None:
       return ws
     pk = self.pk
     T, H, C = pk.T, pk.H, pk.channels
     u8 = dict(device=self.device, dtype=torch.uint8)
+    f32 = dict(device=self.device, dtype=torch.float32)
     ws = {
-        "s1": torch.empty((Bc, T, H // 2, H // 2, C), **u8),
-        "s2": torch.empty((Bc, T, H // 4, H // 4, C), **u8),
-        "s3": torch.empty((Bc, T, H // 8, H // 8, C), **u8),
-        "s4": torch.empty((Bc, T, H // 8, H // 8, C), **u8),     # un-pooled (TCJA input)
-        "p4": torch.empty((Bc, T, H // 16, H // 16, C), **u8),
-        "s5": torch.empty((Bc, T, H // 16, H // 16, C), **u8),   # un-pooled
-        "p5": torch.empty((Bc, T, H // 32, H // 32, C), **u8),
-        "att4": torch.empty((Bc, T, C), device=self.device, dtype=torch.float32),
-        "att5": torch.empty((Bc, T, C), device=self.device, dtype=torch.float32),
-        "cnt": torch.empty((Bc, T, C), device=self.device, dtype=torch.int32),
-        "d1": torch.empty((Bc, T, pk.dense1.cout), **u8),
-        "d2": torch.empty((Bc, T, pk.dense2.cout), **u8),
+        "s1": torch.empty((Bc, T, H // 2, H // 2, C), **u8),     # per chunk
+        "s2": torch.empty((Bc, T, H // 4, H // 4, C), **u8),     # per chunk
+        "s3": torch.empty((B, T, H // 8, H // 8, C), **u8),      # whole batch from here on
+        "p4": torch.empty((B, T, H // 16, H // 16, C), **u8),
+        "p5": torch.empty((B, T, H // 32, H // 32, C), **u8),
+        "att4": torch.empty((B, T, C), **f32),
+        "att5": torch.empty((B, T, C), **f32),
+        "cnt4": torch.zeros((B, T, C), device=self.device, dtype=torch.int32),
+        "cnt5": torch.zeros((B, T, C), device=self.device, dtype=torch.int32),
+        "d1": torch.empty((B, T, pk.dense1.cout), **u8),
+        "d2": torch.empty((B, T, pk.dense2.cout), **u8),
     }
-    self._ws[Bc] = ws
+    self._ws[key] = ws
     return ws
 
-  def _bp(self, Bc, H, Cin, Cout, x: torch.Tensor, y: Optional[torch.Tensor],
-          pool: int, att: Optional[torch.Tensor] = None, att_mod: int = 0, impl=None) -> BlockParams:
+  def _bp(self, B, H, Cin, Cout, x: torch.Tensor, y: Optional[torch.Tensor],
+          pool: int, att: Optional[torch.Tensor] = None, att_mod: int = 0) -> BlockParams:
     p = BlockParams()
-    p.T, p.B, p.H, p.W, p.Cin, p.Cout = self.pk.T, Bc, H, H, Cin, Cout
+    p.T, p.B, p.H, p.W, p.Cin, p.Cout = self.pk.T, B, H, H, Cin, Cout
     p.x_stride_b, p.x_stride_t = x.stride(0) * x.element_size(), x.stride(1) * x.element_size()
     if y is not None:
       p.y_stride_b, p.y_stride_t = y.stride(0) * y.element_size(), y.stride(1) * y.element_size()
@@ -71,89 +78,131 @@ class CextNetEngine:
     p.att_mod = att_mod
     p.tau, p.v_threshold, p.v_reset = self.tau, self.v_th, self.v_reset
     p.pool = pool
-    p.impl = self.impl if impl is None else impl
+    p.impl = self.impl
     return p
 
-  # -- one chunk -------------------------------------------------------------
-  def _forward_chunk(self, frames: torch.Tensor, logits: torch.Tensor,
-                     collect: Optional[Dict[str, torch.Tensor]] = None) -> None:
-    L = _lib.lib()
+  # -- launches --------------------------------------------------------------
+  def _conv(self, i, x, y, B, Hin, Cin, pool, att=None, counts=None, collect=None, key=None):
+    L, P = _lib.lib(), _lib.ptr
+    pk, C = self.pk, self.pk.channels
+    lay = pk.convs[i]
+    p = self._bp(B, Hin, Cin, C, x, y, pool, att, C)
+    dump = u = None
+    if collect is not None and key is not None:
+      dt = torch.float32 if att is not None else torch.int32
+      dump = torch.empty((pk.T, B, Hin, Hin, C), device=self.device, dtype=dt)
+      u = torch.empty((B, Hin, Hin, C), device=self.device, dtype=torch.float32)
+      collect[key + "_acc"], collect[key + "_u"] = dump, u
+    _lib.check(L.snnqp_spiking_conv3x3_counts_fwd(p, P(x), P(att), P(lay.wq), P(lay.scale), P(lay.bias),
+                                                  P(y), P(u), P(dump), P(counts), _lib.stream()))
+
+  def _tcja(self, i, B, Hs, spikes, counts, att):
+    L, P = _lib.lib(), _lib.ptr
+    tj, C = self.pk.tcja[i], self.pk.channels
+    p = self._bp(B, Hs, C, C, spikes if spikes is not None else att, None, 0, att, C)
+    _lib.check(L.snnqp_tcja_fwd(p, P(spikes), P(tj.wq_t), P(tj.wq_c), P(tj.scale_t), P(tj.scale_c),
+                                P(counts), P(att), _lib.stream()))
+
+  def _pool(self, B, x, y, Hin):
+    C = self.pk.channels
+    p = self._bp(B, Hin, C, C, x, y, 1)
+    _lib.check(_lib.lib().snnqp_maxpool2_fwd(p, _lib.ptr(x), _lib.ptr(y), _lib.stream()))
+
+  def _dense(self, lay, B, x, att, y, collect=None, key=None):
+    L, P = _lib.lib(), _lib.ptr
+    p = self._bp(B, 1, lay.cin, lay.cout, x, y, 0, att, self.pk.channels)
+    dump = u = None
+    if collect is not None and key is not None:
+      dt = torch.float32 if att is not None else torch.int32
+      dump = torch.empty((self.pk.T, B, lay.cout), device=self.device, dtype=dt)
+      u = torch.empty((B, lay.cout), device=self.device, dtype=torch.float32)
+      collect[key + "_acc"], collect[key + "_u"] = dump, u
+    _lib.check(L.snnqp_spiking_dense_fwd(p, P(x), P(att), P(lay.wq), P(lay.scale), P(lay.bias),
+                                         P(y), P(u), P(dump), _lib.stream()))
+
+  # -- forward ---------------------------------------------------------------
+  def _run(self, frames: torch.Tensor, logits: torch.Tensor,
+           collect: Optional[Dict[str, torch.Tensor]] = None) -> None:
     pk = self.pk
-    Bc = frames.shape[0]
-    H, C = pk.H, pk.channels
-    ws = self._workspace(Bc)
-    st = _lib.stream()
-    P = _lib.ptr
+    B = frames.shape[0]
+    H, C, T = pk.H, pk.channels, pk.T
+    Bc = min(self.chunk, B)
+    ws = self._workspace(B, Bc)
 
-    def conv(i, x, y, Hin, Cin, pool, att=None, key=None):
-      lay = pk.convs[i]
-      p = self._bp(Bc, Hin, Cin, C, x, y, pool, att, C)
-      dump = u = None
-      if collect is not None and key is not None:
-        dt = torch.float32 if att is not None else torch.int32
-        dump = torch.empty((pk.T, Bc, Hin, Hin, C), device=self.device, dtype=dt)
-        u = torch.empty((Bc, Hin, Hin, C), device=self.device, dtype=torch.float32)
-        collect[key + "_acc"], collect[key + "_u"] = dump, u
-      _lib.check(L.snnqp_spiking_conv3x3_fwd(p, P(x), P(att), P(lay.wq), P(lay.scale), P(lay.bias),
-                                             P(y), P(u), P(dump), st))
+    # head: conv1 -> conv2 -> conv3, chunk by chunk
+    for b0 in range(0, B, Bc):
+      n = min(Bc, B - b0)
+      s1, s2 = ws["s1"][:n], ws["s2"][:n]
+      self._conv(0, frames[b0:b0 + n], s1, n, H, 2, 1, collect=collect, key="conv1")
+      self._conv(1, s1, s2, n, H // 2, C, 1, collect=collect, key="conv2")
+      self._conv(2, s2, ws["s3"][b0:b0 + n], n, H // 4, C, 1, collect=collect, key="conv3")
 
-    def tcja(i, s, Hs, att):
-      tj = pk.tcja[i]
-      p = self._bp(Bc, Hs, C, C, s, None, 0, att, C)
-      _lib.check(L.snnqp_tcja_fwd(p, P(s), P(tj.wq_t), P(tj.wq_c), P(tj.scale_t), P(tj.scale_c),
-                                  P(ws["cnt"]), P(att), st))
+    if collect is None:
+      # tail, fused: pooled spikes + spike counts straight from the conv epilogues
+      ws["cnt4"].zero_(); ws["cnt5"].zero_()
+      self._conv(3, ws["s3"], ws["p4"], B, H // 8, C, 1, counts=ws["cnt4"])
+      self._tcja(0, B, H // 8, None, ws["cnt4"], ws["att4"])
+      self._conv(4, ws["p4"], ws["p5"], B, H // 16, C, 1, att=ws["att4"], counts=ws["cnt5"])
+      self._tcja(1, B, H // 16, None, ws["cnt5"], ws["att5"])
+    else:
+      # instrumented tail: un-pooled spikes are materialised so every intermediate can be compared
+      dev = self.device
+      s4 = torch.empty((B, T, H // 8, H // 8, C), device=dev, dtype=torch.uint8)
+      s5 = torch.empty((B, T, H // 16, H // 16, C), device=dev, dtype=torch.uint8)
+      self._conv(3, ws["s3"], s4, B, H // 8, C, 0, collect=collect, key="conv4")
+      self._tcja(0, B, H // 8, s4, ws["cnt4"], ws["att4"])
+      self._pool(B, s4, ws["p4"], H // 8)
+      self._conv(4, ws["p4"], s5, B, H // 16, C, 0, att=ws["att4"], collect=collect, key="conv5")
+      self._tcja(1, B, H // 16, s5, ws["cnt5"], ws["att5"])
+      self._pool(B, s5, ws["p5"], H // 16)
+      collect["s4"], collect["s5"] = s4, s5
 
-    def pool(x, y, Hin):
-      p = self._bp(Bc, Hin, C, C, x, y, 1)
-      _lib.check(L.snnqp_maxpool2_fwd(p, P(x), P(y), st))
-
-    def dense(lay, x, att, y, key=None):
-      p = self._bp(Bc, 1, lay.cin, lay.cout, x, y, 0, att, C)
-      p.W = 1
-      dump = u = None
-      if collect is not None and key is not None:
-        dt = torch.float32 if att is not None else torch.int32
-        dump = torch.empty((pk.T, Bc, lay.cout), device=self.device, dtype=dt)
-        u = torch.empty((Bc, lay.cout), device=self.device, dtype=torch.float32)
-        collect[key + "_acc"], collect[key + "_u"] = dump, u
-      _lib.check(L.snnqp_spiking_dense_fwd(p, P(x), P(att), P(lay.wq), P(lay.scale), P(lay.bias),
-                                           P(y), P(u), P(dump), st))
-
-    conv(0, frames, ws["s1"], H, 2, 1, key="conv1")
-    conv(1, ws["s1"], ws["s2"], H // 2, C, 1, key="conv2")
-    conv(2, ws["s2"], ws["s3"], H // 4, C, 1, key="conv3")
-    conv(3, ws["s3"], ws["s4"], H // 8, C, 0, key="conv4")
-    tcja(0, ws["s4"], H // 8, ws["att4"])
-    pool(ws["s4"], ws["p4"], H // 8)
-    conv(4, ws["p4"], ws["s5"], H // 16, C, 0, att=ws["att4"], key="conv5")
-    tcja(1, ws["s5"], H // 16, ws["att5"])
-    pool(ws["s5"], ws["p5"], H // 16)
-    x_d1 = ws["p5"].view(Bc, pk.T, -1)
-    dense(pk.dense1, x_d1, ws["att5"], ws["d1"], key="dense1")
-    dense(pk.dense2, ws["d1"], None, ws["d2"], key="dense2")
+    self._dense(pk.dense1, B, ws["p5"].view(B, T, -1), ws["att5"], ws["d1"], collect, "dense1")
+    self._dense(pk.dense2, B, ws["d1"], None, ws["d2"], collect, "dense2")
     d2 = ws["d2"]
-    _lib.check(L.snnqp_vote_fwd(P(d2), pk.T, Bc, pk.dense2.cout, 10, d2.stride(1), d2.stride(0),
-                                P(logits), st))
+    _lib.check(_lib.lib().snnqp_vote_fwd(_lib.ptr(d2), T, B, pk.dense2.cout, 10, d2.stride(1), d2.stride(0),
+                                         _lib.ptr(logits), _lib.stream()))
     if collect is not None:
-      for k in ("s1", "s2", "s3", "s4", "p4", "s5", "p5", "att4", "att5", "d1", "d2"):
+      for k in ("s1", "s2", "s3", "p4", "p5", "att4", "att5", "d1", "d2"):
         collect[k] = ws[k].clone()
 
-  # -- public ----------------------------------------------------------------
+  def _check(self, frames: torch.Tensor) -> None:
+    if not frames.is_cuda or frames.dtype != torch.uint8:
+      raise ValueError("frames must be a uint8 CUDA tensor (B,T,H,W,2); no CPU fallback")
+    pk = self.pk
+    if tuple(frames.shape[1:]) != (pk.T, pk.H, pk.H, 2):
+      raise ValueError(f"frames shape {tuple(frames.shape)} != (B,{pk.T},{pk.H},{pk.H},2)")
+
   def forward(self, frames: torch.Tensor, collect: Optional[Dict[str, torch.Tensor]] = None
               ) -> torch.Tensor:
     """frames: uint8 CUDA tensor (B,T,H,W,2) of event counts.  Returns fp32
     logits (B, num_classes) on the device (no host sync)."""
-    if not frames.is_cuda or frames.dtype != torch.uint8:
-      raise ValueError("frames must be a uint8 CUDA tensor (B,T,H,W,2); no CPU fallback")
-    pk = self.pk
-    B = frames.shape[0]
-    if tuple(frames.shape[1:]) != (pk.T, pk.H, pk.H, 2):
-      raise ValueError(f"frames shape {tuple(frames.shape)} != (B,{pk.T},{pk.H},{pk.H},2)")
+    self._check(frames)
     frames = frames.contiguous()
-    logits = torch.empty((B, pk.num_classes), device=self.device, dtype=torch.float32)
+    B = frames.shape[0]
     if collect is not None and B > self.chunk:
       raise ValueError("collect= needs B <= chunk")
-    for b0 in range(0, B, self.chunk):
-      b1 = min(B, b0 + self.chunk)
-      self._forward_chunk(frames[b0:b1], logits[b0:b1], collect)
+    logits = torch.empty((B, self.pk.num_classes), device=self.device, dtype=torch.float32)
+    self._run(frames, logits, collect)
     return logits
+
+  def forward_graph(self, frames: torch.Tensor) -> torch.Tensor:
+    """Same as :meth:`forward`, replayed from a CUDA graph captured on the first
+    call for this (buffer, batch) -- removes the per-launch host overhead.  The
+    returned logits tensor is static (overwritten by the next replay)."""
+    self._check(frames)
+    if not frames.is_contiguous():
+      raise ValueError("forward_graph needs a contiguous frames buffer")
+    key = (frames.data_ptr(), frames.shape[0])
+    ent = self._graphs.get(key)
+    if ent is None:
+      logits = torch.empty((frames.shape[0], self.pk.num_classes), device=self.device, dtype=torch.float32)
+      self._run(frames, logits)                 # eager warm-up: function attributes, workspaces
+      torch.cuda.synchronize()
+      g = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(g):
+        self._run(frames, logits)
+      ent = (g, logits, frames)
+      self._graphs[key] = ent
+    ent[0].replay()
+    return ent[1]

@@ -124,7 +124,7 @@ def test_fold_affine_bit_exact(cuda_lib):
 
 
 # ------------------------------------------------------- fused conv block ----
-def run_conv(lib, x_tb, wq, scale, bias, Cout, pool, impl, att=None, tau=2.0, batch_major=False):
+def run_conv(lib, x_tb, wq, scale, bias, Cout, pool, impl, att=None, tau=2.0, batch_major=False, counts=None):
   """x_tb: numpy (T,B,H,W,Cin) u8.  Calls snnqp_spiking_conv3x3_fwd through the
   C-ABI; returns numpy (spikes (T,B,Ho,Wo,C), u (B,H,W,C), acc (T,B,H,W,C))."""
   T, B, H, W, Cin = x_tb.shape
@@ -149,8 +149,12 @@ def run_conv(lib, x_tb, wq, scale, bias, Cout, pool, impl, att=None, tau=2.0, ba
   p.att_mod = Cin
   p.tau, p.v_threshold, p.v_reset = tau, 1.0, 0.0
   p.pool, p.impl = int(pool), impl
-  _lib.check(lib.snnqp_spiking_conv3x3_fwd(p, P(xs), P(attd), P(wq), P(scale), P(bias), P(spikes), P(u),
-                                           P(acc), _lib.stream()))
+  if counts is None:
+    _lib.check(lib.snnqp_spiking_conv3x3_fwd(p, P(xs), P(attd), P(wq), P(scale), P(bias), P(spikes), P(u),
+                                             P(acc), _lib.stream()))
+  else:
+    _lib.check(lib.snnqp_spiking_conv3x3_counts_fwd(p, P(xs), P(attd), P(wq), P(scale), P(bias), P(spikes), P(u),
+                                                    P(acc), P(counts), _lib.stream()))
   torch.cuda.synchronize()
   return spikes.cpu().numpy(), u.cpu().numpy(), acc.cpu().numpy()
 
@@ -218,8 +222,10 @@ def test_spiking_conv_binary_bit_exact(cuda_lib, oracle_lib, impl, shape, bits, 
   packed = pk_mod.pack_conv3x3(lay, bits, DEV, bn, stt)
   scale, bias = ref_int.fold_affine(lay["DuQ_0"]["c"], bits, bn, stt, 128)
   s_ref, info = ref_int.spiking_conv3x3(x, q, scale, bias, pool=pool, want=True)
+  cnt = torch.zeros((B, T, 128), device=DEV, dtype=torch.int32)
   try:
-    s, u, acc = run_conv(cuda_lib, x, packed.wq, packed.scale, packed.bias, 128, pool, impl, batch_major=True)
+    s, u, acc = run_conv(cuda_lib, x, packed.wq, packed.scale, packed.bias, 128, pool, impl, batch_major=True,
+                         counts=cnt)
   except _lib.SnnqpError as e:
     if impl == _lib.IMPL_TCGEN05 and e.code == 3:
       pytest.skip("shape outside the tcgen05 kernel's envelope: " + str(e))
@@ -227,6 +233,7 @@ def test_spiking_conv_binary_bit_exact(cuda_lib, oracle_lib, impl, shape, bits, 
   assert np.array_equal(acc, info["acc"]), "int32 accumulators differ"
   assert np.array_equal(s, s_ref), f"spike flips: {np.mean(s != s_ref)}"
   assert np.array_equal(u, info["u"]), "membrane differs"
+  assert np.array_equal(cnt.cpu().numpy(), info["spikes"].sum(axis=(2, 3), dtype=np.int32).transpose(1, 0, 2))
   assert 0.02 < s_ref.mean() < 0.9
 
 
@@ -241,26 +248,34 @@ def test_spiking_conv_tau_not_power_of_two_and_extremes(cuda_lib, oracle_lib):
     assert np.array_equal(acc, info["acc"]) and np.array_equal(s, s_ref) and np.array_equal(u, info["u"])
 
 
-def test_spiking_conv_att_within_tolerance(cuda_lib, oracle_lib):
-  """conv5: real-valued input att * spikes; fp32 accumulation order differs from
-  the float64 oracle -> membrane <= 1e-5 relative, flips <= 1e-4."""
+@pytest.mark.parametrize("impl", impls())
+@pytest.mark.parametrize("pool", [False, True])
+def test_spiking_conv_att_within_tolerance(cuda_lib, oracle_lib, impl, pool):
+  """conv5: real-valued input att * spikes.  SIMT: fp32 FMAs (summation order differs
+  from the float64 oracle); tcgen05: 24-bit fixed-point attention as three exact
+  int8 contractions.  Bar: membrane <= 1e-5 relative, flips <= 1e-4."""
   rng = np.random.default_rng(31)
-  T, B, H = 4, 2, 8
+  T, B, H = 4, 3, 8
   lay, q, bn, stt = make_layer(rng, 128, 128, 8, 0.5)
   x = (rng.uniform(size=(T, B, H, H, 128)) < 0.3).astype(np.uint8)
-  att = rng.uniform(0.05, 1.0, size=(T, B, 128)).astype(F32)
+  att = rng.uniform(0.0, 1.0, size=(T, B, 128)).astype(F32)
+  att[0, 0, :4] = [1.0, 0.0, 1e-8, 0.99999994]                 # saturated / vanishing attention
   packed = pk_mod.pack_conv3x3(lay, 8, DEV, bn, stt)
   scale, bias = ref_int.fold_affine(lay["DuQ_0"]["c"], 8, bn, stt, 128)
   accf = ref_int.conv3x3_att_accf(x, att, q)
   s_ref, u_ref = ref_int.lif_from_acc(accf, scale, bias)
-  s, u, acc = run_conv(cuda_lib, x, packed.wq, packed.scale, packed.bias, 128, False, _lib.IMPL_SIMT, att=att)
+  cnt = torch.zeros((B, T, 128), device=DEV, dtype=torch.int32)
+  s, u, acc = run_conv(cuda_lib, x, packed.wq, packed.scale, packed.bias, 128, pool, impl, att=att,
+                       batch_major=True, counts=cnt)
   assert preact_err(acc, accf, scale, bias) <= 1e-5
-  assert np.mean(s != s_ref) <= 1e-4
-  same = (s == s_ref).all(axis=0)
-  assert np.max((np.abs(u - u_ref) / np.maximum(np.abs(u_ref), 1.0))[same]) <= 1e-5
-  # and given the kernel's own accumulators the epilogue is bit-exact
+  # given the kernel's own accumulators the epilogue (LIF, pool, counts) is bit-exact
   s2, u2 = ref_int.lif_from_acc(acc, scale, bias)
-  assert np.array_equal(s, s2) and np.array_equal(u, u2)
+  assert np.array_equal(u, u2)
+  assert np.array_equal(s, ref_int.maxpool2_u8(s2) if pool else s2)
+  assert np.array_equal(cnt.cpu().numpy(), s2.sum(axis=(2, 3), dtype=np.int32).transpose(1, 0, 2))
+  assert np.mean(s2 != s_ref) <= 1e-4
+  same = (s2 == s_ref).all(axis=0)
+  assert np.max((np.abs(u - u_ref) / np.maximum(np.abs(u_ref), 1.0))[same]) <= 1e-5
 
 
 def test_qconv_plain_forward(cuda_lib, oracle_lib):
@@ -279,29 +294,33 @@ def test_qconv_plain_forward(cuda_lib, oracle_lib):
 
 
 # ------------------------------------------------------------ dense / tcja ----
-def run_dense(lib, x, wq, scale, bias, N, att=None, att_mod=0):
+def run_dense(lib, x, wq, scale, bias, N, att=None, att_mod=0, impl=_lib.IMPL_SIMT):
+  """x: numpy (T,B,K); the device copy is batch-major [B][T][K] (rows (b,t) contiguous)."""
   T, B, K = x.shape
-  xs = dev(x)
+  xs = dev(np.ascontiguousarray(np.swapaxes(x, 0, 1)))
   spikes = torch.empty((T, B, N), device=DEV, dtype=torch.uint8)
   u = torch.empty((B, N), device=DEV, dtype=torch.float32)
   acc = torch.empty((T, B, N), device=DEV, dtype=torch.float32 if att is not None else torch.int32)
   p = BlockParams()
   p.T, p.B, p.H, p.W, p.Cin, p.Cout = T, B, 1, 1, K, N
-  p.x_stride_t, p.x_stride_b = xs.stride(0), xs.stride(1)
+  p.x_stride_t, p.x_stride_b = xs.stride(1), xs.stride(0)
   p.y_stride_t, p.y_stride_b = spikes.stride(0), spikes.stride(1)
   attd = None
   if att is not None:
     attd = dev(att); p.att_stride_t, p.att_stride_b = attd.stride(0), attd.stride(1)
   p.att_mod = att_mod
   p.tau, p.v_threshold, p.v_reset = 2.0, 1.0, 0.0
+  p.impl = impl
   _lib.check(lib.snnqp_spiking_dense_fwd(p, P(xs), P(attd), P(wq), P(scale), P(bias), P(spikes), P(u), P(acc),
                                          _lib.stream()))
   torch.cuda.synchronize()
   return spikes.cpu().numpy(), u.cpu().numpy(), acc.cpu().numpy()
 
 
-@pytest.mark.parametrize("T,B,K,N,bits", [(5, 3, 512, 110, 8), (3, 9, 100, 40, 4), (2, 1, 2048, 512, 2)])
-def test_spiking_dense_binary_bit_exact(cuda_lib, oracle_lib, T, B, K, N, bits):
+@pytest.mark.parametrize("impl", impls())
+@pytest.mark.parametrize("T,B,K,N,bits", [(5, 3, 512, 110, 8), (3, 9, 100, 40, 4), (2, 1, 2048, 512, 2),
+                                          (20, 19, 512, 110, 8), (4, 45, 256, 300, 8)])
+def test_spiking_dense_binary_bit_exact(cuda_lib, oracle_lib, impl, T, B, K, N, bits):
   rng = np.random.default_rng(K + N)
   k = (rng.standard_normal((K, N)) * (5.0 / np.sqrt(K))).astype(F32)
   mask = ref_quant.local_mask(k, 0.5)
@@ -313,14 +332,21 @@ def test_spiking_dense_binary_bit_exact(cuda_lib, oracle_lib, T, B, K, N, bits):
   x = (rng.uniform(size=(T, B, K)) < 0.2).astype(np.uint8)
   acc_ref = ref_int.dense_acc(x, q)
   s_ref, u_ref = ref_int.lif_from_acc(acc_ref, scale, bias)
-  s, u, acc = run_dense(cuda_lib, x, packed.wq, packed.scale, packed.bias, N)
+  try:
+    s, u, acc = run_dense(cuda_lib, x, packed.wq, packed.scale, packed.bias, N, impl=impl)
+  except _lib.SnnqpError as e:
+    if impl == _lib.IMPL_TCGEN05 and e.code == 3:
+      pytest.skip("shape outside the tcgen05 dense kernel's envelope: " + str(e))
+    raise
   assert np.array_equal(acc, acc_ref) and np.array_equal(s, s_ref) and np.array_equal(u, u_ref)
   assert s_ref.mean() > 0.01
 
 
-def test_spiking_dense_att_within_tolerance(cuda_lib, oracle_lib):
+@pytest.mark.parametrize("impl", impls())
+@pytest.mark.parametrize("T,B", [(4, 5), (20, 11)])
+def test_spiking_dense_att_within_tolerance(cuda_lib, oracle_lib, impl, T, B):
   rng = np.random.default_rng(55)
-  T, B, K, N, Cc = 4, 5, 2048, 512, 128
+  K, N, Cc = 2048, 512, 128
   k = (rng.standard_normal((K, N)) * (7.0 / np.sqrt(K))).astype(F32)
   a = ref_quant.gaussian_init(k, 8)
   lay = {"kernel": k, "DuQ_0": {"a": np.array([a], F32), "c": np.array([a], F32)},
@@ -333,7 +359,7 @@ def test_spiking_dense_att_within_tolerance(cuda_lib, oracle_lib):
   att_k = np.tile(att, (1, 1, K // Cc))                       # k % 128 -> channel
   accf = ref_int.dense_att_accf(x, att_k, q)
   s_ref, u_ref = ref_int.lif_from_acc(accf, scale, bias)
-  s, u, acc = run_dense(cuda_lib, x, packed.wq, packed.scale, packed.bias, N, att=att, att_mod=Cc)
+  s, u, acc = run_dense(cuda_lib, x, packed.wq, packed.scale, packed.bias, N, att=att, att_mod=Cc, impl=impl)
   assert preact_err(acc, accf, scale, bias) <= 1e-5
   assert np.mean(s != s_ref) <= 1e-4
   s2, u2 = ref_int.lif_from_acc(acc, scale, bias)
@@ -455,6 +481,22 @@ def test_network_layerwise_teacher_forced_and_float_path(cuda_lib, oracle_lib):
     rel = np.abs(ug - uf) / np.maximum(np.abs(uf), 1.0)
     assert np.quantile(rel, 0.9999) <= 1e-5, i
   assert np.max(np.abs(logits - lf)) <= 1e-2
+
+
+def test_fused_tail_equals_instrumented_tail(cuda_lib):
+  """The production forward (pooled spikes + spike counts fused into the conv
+  epilogues, no un-pooled tensors) must give exactly the logits of the
+  instrumented forward that materialises every intermediate; so must a CUDA-graph replay."""
+  bits, T, H, B = 8, 20, 128, 3
+  v = synthetic.make_variables(bits=bits, prune_percentage=0.5, T=T, H=H, seed=1)
+  frd = dev(synthetic.make_frames(B, T, H, H, seed=4))
+  eng = engine_for(v, bits, T, H)
+  l_fused = eng.forward(frd).cpu().numpy()
+  l_inst = eng.forward(frd, collect={}).cpu().numpy()
+  assert np.array_equal(l_fused, l_inst)
+  l_graph = eng.forward_graph(frd).cpu().numpy()
+  l_graph2 = eng.forward_graph(frd).cpu().numpy()
+  assert np.array_equal(l_graph, l_fused) and np.array_equal(l_graph2, l_fused)
 
 
 def test_full_size_properties(cuda_lib):
