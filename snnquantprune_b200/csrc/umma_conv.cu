@@ -23,6 +23,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "epilogue.cuh"
 #include "ptx.cuh"
 
 namespace snnqp {
@@ -62,7 +63,9 @@ template <> struct Cfg<64> { static constexpr int TH = 2, R = 2, WC = 32; };
 template <> struct Cfg<32> { static constexpr int TH = 4, R = 2, WC = 32; };
 template <> struct Cfg<16> { static constexpr int TH = 8, R = 4, WC = 16; };
 
-template <int WCFG, bool TAU2>
+// FAST: standard LIF constants (tau 2, threshold 1, reset 0), pooled output, no
+// instrumentation outputs -- the production variant; !FAST handles everything else.
+template <int WCFG, bool FAST, bool COUNTS>
 __global__ void __launch_bounds__(kThreads, 1)
 k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                const UmmaArgs a) {
@@ -191,22 +194,39 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(acc_empty + s);        // TMEM buffer free for step + 2
 
+        if constexpr (FAST) {
+          const LifParams<true> lif{2.0f, 1.0f, 0.0f};
+          uint8_t *y0 = a.spikes + (int64_t)t * a.y_stride_t + (int64_t)b * a.y_stride_b + c;
+          int nspk = 0;
+#pragma unroll
+          for (int pr = 0; pr < R / 2; ++pr) {
+            uint8_t *yrow = y0 + ((int64_t)((h0 + r0 + 2 * pr) >> 1) * Wo + (w0 >> 1)) * kC;
+#pragma unroll
+            for (int pc = 0; pc < WC / 2; ++pc) {
+              bool any = false;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int r = 2 * pr + (e >> 1), j = 2 * pc + (e & 1);
+                const bool sp = lif.step(u[r][j], __fmaf_rn((float)(int32_t)acc[r][j], sc, bi));
+                any |= sp;
+                if constexpr (COUNTS) nspk += sp ? 1 : 0;
+              }
+              yrow[pc * kC] = any ? 1 : 0;
+            }
+          }
+          if constexpr (COUNTS) {
+            if (nspk) atomicAdd(a.counts + ((int64_t)b * a.T + t) * kC + c, nspk);
+          }
+          continue;
+        }
+        const LifParams<false> lif{a.tau, a.v_th, a.v_reset};
         uint32_t m[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           m[r] = 0;
 #pragma unroll
           for (int j = 0; j < WC; ++j) {
-            const float v = __fmaf_rn((float)(int32_t)acc[r][j], sc, bi);
-            bool sp;
-            if constexpr (TAU2) {
-              // tau == 2: (x - (u - v_reset)) / 2 == * 0.5 exactly (same rounding as the division)
-              const float un = __fadd_rn(u[r][j], __fmul_rn(__fsub_rn(v, __fsub_rn(u[r][j], a.v_reset)), 0.5f));
-              sp = __fsub_rn(un, a.v_th) >= 0.0f;
-              u[r][j] = sp ? a.v_reset : un;
-            } else {
-              u[r][j] = lif_step(u[r][j], v, a.tau, a.v_th, a.v_reset, sp);
-            }
+            const bool sp = lif.step(u[r][j], __fmaf_rn((float)(int32_t)acc[r][j], sc, bi));
             m[r] |= (sp ? 1u : 0u) << j;
           }
         }
@@ -360,16 +380,23 @@ int launch_conv3x3_umma(const snnqp_block_params &p, const uint8_t *x, const int
   a.spikes = spikes; a.u_final = u_final; a.acc_dump = acc_dump; a.counts = counts;
 
   const int grid = a.total_items < sm_count() ? a.total_items : sm_count();
-  const bool tau2 = (p.tau == 2.0f);
-#define SNNQP_LAUNCH_UMMA(WV, T2)                                                                          \
-  do {                                                                                                     \
-    SNNQP_CUDA(cudaFuncSetAttribute(k_conv3x3_umma<WV, T2>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                    kSmemBytes));                                                          \
-    k_conv3x3_umma<WV, T2><<<grid, kThreads, kSmemBytes, st>>>(tmx, tmw, a);                               \
+  const bool fast = p.tau == 2.0f && p.v_threshold == 1.0f && p.v_reset == 0.0f && p.pool && !u_final && !acc_dump;
+#define SNNQP_LAUNCH_UMMA(WV, FA, CO)                                                                          \
+  do {                                                                                                         \
+    SNNQP_CUDA(cudaFuncSetAttribute(k_conv3x3_umma<WV, FA, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                    kSmemBytes));                                                              \
+    k_conv3x3_umma<WV, FA, CO><<<grid, kThreads, kSmemBytes, st>>>(tmx, tmw, a);                               \
   } while (0)
-  if (p.W == 64) { if (tau2) SNNQP_LAUNCH_UMMA(64, true); else SNNQP_LAUNCH_UMMA(64, false); }
-  else if (p.W == 32) { if (tau2) SNNQP_LAUNCH_UMMA(32, true); else SNNQP_LAUNCH_UMMA(32, false); }
-  else { if (tau2) SNNQP_LAUNCH_UMMA(16, true); else SNNQP_LAUNCH_UMMA(16, false); }
+#define SNNQP_LAUNCH_UMMA_W(WV)                                             \
+  do {                                                                      \
+    if (!fast) SNNQP_LAUNCH_UMMA(WV, false, false);                         \
+    else if (counts) SNNQP_LAUNCH_UMMA(WV, true, true);                     \
+    else SNNQP_LAUNCH_UMMA(WV, true, false);                                \
+  } while (0)
+  if (p.W == 64) SNNQP_LAUNCH_UMMA_W(64);
+  else if (p.W == 32) SNNQP_LAUNCH_UMMA_W(32);
+  else SNNQP_LAUNCH_UMMA_W(16);
+#undef SNNQP_LAUNCH_UMMA_W
 #undef SNNQP_LAUNCH_UMMA
   SNNQP_POST_LAUNCH("k_conv3x3_umma");
   return SNNQP_OK;

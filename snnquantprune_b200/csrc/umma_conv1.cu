@@ -19,6 +19,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "epilogue.cuh"
 #include "ptx.cuh"
 
 namespace snnqp {
@@ -60,7 +61,9 @@ __device__ __forceinline__ uint32_t sw128_off(int row, int chunk) {
   return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
 }
 
-template <bool TAU2>
+// FAST: standard LIF constants (tau 2, threshold 1, reset 0), pooled output, no
+// instrumentation outputs -- the production variant; !FAST handles everything else.
+template <bool FAST>
 __global__ void __launch_bounds__(kThreads, 1)
 k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
   extern __shared__ uint8_t smem_raw[];
@@ -203,25 +206,31 @@ k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(acc_empty + s);
 
+        uint8_t *yb = a.spikes + (int64_t)t * a.y_stride_t + (int64_t)b * a.y_stride_b + c;
+        if constexpr (FAST) {
+          const LifParams<true> lif{2.0f, 1.0f, 0.0f};
+          uint8_t *yrow = yb + ((int64_t)qh * Wo + qw0) * kC;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            bool any = false;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              any |= lif.step(u[j][i], __fmaf_rn((float)(int32_t)acc[j][i], sc, bi));
+            yrow[i * kC] = any ? 1 : 0;
+          }
+          continue;
+        }
+        const LifParams<false> lif{a.tau, a.v_th, a.v_reset};
         uint32_t m[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           m[j] = 0;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float v = __fmaf_rn((float)(int32_t)acc[j][i], sc, bi);
-            bool sp;
-            if constexpr (TAU2) {
-              const float un = __fadd_rn(u[j][i], __fmul_rn(__fsub_rn(v, __fsub_rn(u[j][i], a.v_reset)), 0.5f));
-              sp = __fsub_rn(un, a.v_th) >= 0.0f;
-              u[j][i] = sp ? a.v_reset : un;
-            } else {
-              u[j][i] = lif_step(u[j][i], v, a.tau, a.v_th, a.v_reset, sp);
-            }
+            const bool sp = lif.step(u[j][i], __fmaf_rn((float)(int32_t)acc[j][i], sc, bi));
             m[j] |= (sp ? 1u : 0u) << i;
           }
         }
-        uint8_t *yb = a.spikes + (int64_t)t * a.y_stride_t + (int64_t)b * a.y_stride_b + c;
         if (a.pool) {
           const uint32_t mm = m[0] | m[1] | m[2] | m[3];
 #pragma unroll
@@ -325,7 +334,8 @@ int launch_conv1_umma(const snnqp_block_params &p, const uint8_t *x, const int8_
   a.spikes = spikes; a.u_final = u_final; a.acc_dump = acc_dump;
   const int grid = a.total_items < sm_count() ? a.total_items : sm_count();
   constexpr int kSmem = 4 * kWjBytes + kBStages * kBBytes + kStStages * kStBytes + 256 + 1024;
-  if (p.tau == 2.0f) {
+  const bool fast = p.tau == 2.0f && p.v_threshold == 1.0f && p.v_reset == 0.0f && p.pool && !u_final && !acc_dump;
+  if (fast) {
     SNNQP_CUDA(cudaFuncSetAttribute(k_conv1_umma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     k_conv1_umma<true><<<grid, kThreads, kSmem, st>>>(tmx, a);
   } else {

@@ -124,7 +124,8 @@ def test_fold_affine_bit_exact(cuda_lib):
 
 
 # ------------------------------------------------------- fused conv block ----
-def run_conv(lib, x_tb, wq, scale, bias, Cout, pool, impl, att=None, tau=2.0, batch_major=False, counts=None):
+def run_conv(lib, x_tb, wq, scale, bias, Cout, pool, impl, att=None, tau=2.0, batch_major=False, counts=None,
+             dumps=True):
   """x_tb: numpy (T,B,H,W,Cin) u8.  Calls snnqp_spiking_conv3x3_fwd through the
   C-ABI; returns numpy (spikes (T,B,Ho,Wo,C), u (B,H,W,C), acc (T,B,H,W,C))."""
   T, B, H, W, Cin = x_tb.shape
@@ -149,12 +150,13 @@ def run_conv(lib, x_tb, wq, scale, bias, Cout, pool, impl, att=None, tau=2.0, ba
   p.att_mod = Cin
   p.tau, p.v_threshold, p.v_reset = tau, 1.0, 0.0
   p.pool, p.impl = int(pool), impl
+  ud, accd = (u, acc) if dumps else (None, None)      # no instrumentation outputs -> the production (FAST) variant
   if counts is None:
-    _lib.check(lib.snnqp_spiking_conv3x3_fwd(p, P(xs), P(attd), P(wq), P(scale), P(bias), P(spikes), P(u),
-                                             P(acc), _lib.stream()))
+    _lib.check(lib.snnqp_spiking_conv3x3_fwd(p, P(xs), P(attd), P(wq), P(scale), P(bias), P(spikes), P(ud),
+                                             P(accd), _lib.stream()))
   else:
-    _lib.check(lib.snnqp_spiking_conv3x3_counts_fwd(p, P(xs), P(attd), P(wq), P(scale), P(bias), P(spikes), P(u),
-                                                    P(acc), P(counts), _lib.stream()))
+    _lib.check(lib.snnqp_spiking_conv3x3_counts_fwd(p, P(xs), P(attd), P(wq), P(scale), P(bias), P(spikes), P(ud),
+                                                    P(accd), P(counts), _lib.stream()))
   torch.cuda.synchronize()
   return spikes.cpu().numpy(), u.cpu().numpy(), acc.cpu().numpy()
 
@@ -187,6 +189,9 @@ def test_spiking_conv1_tcgen05_bit_exact(cuda_lib, oracle_lib, shape, bits, pool
     assert np.array_equal(acc, info["acc"]), "conv1 int32 accumulators differ"
     assert np.array_equal(s, s_ref)
     assert np.array_equal(u, info["u"])
+    s_fast, _, _ = run_conv(cuda_lib, x, packed.wq, packed.scale, packed.bias, 128, pool, _lib.IMPL_TCGEN05,
+                            batch_major=bm, dumps=False)
+    assert np.array_equal(s_fast, s_ref)
 
 
 @pytest.mark.parametrize("shape,bits,pool", [
@@ -235,6 +240,15 @@ def test_spiking_conv_binary_bit_exact(cuda_lib, oracle_lib, impl, shape, bits, 
   assert np.array_equal(u, info["u"]), "membrane differs"
   assert np.array_equal(cnt.cpu().numpy(), info["spikes"].sum(axis=(2, 3), dtype=np.int32).transpose(1, 0, 2))
   assert 0.02 < s_ref.mean() < 0.9
+  # production variant (no instrumentation outputs): same spikes, same counts
+  cnt.zero_()
+  s_fast, _, _ = run_conv(cuda_lib, x, packed.wq, packed.scale, packed.bias, 128, pool, impl, batch_major=True,
+                          counts=cnt, dumps=False)
+  assert np.array_equal(s_fast, s_ref)
+  assert np.array_equal(cnt.cpu().numpy(), info["spikes"].sum(axis=(2, 3), dtype=np.int32).transpose(1, 0, 2))
+  s_fast, _, _ = run_conv(cuda_lib, x, packed.wq, packed.scale, packed.bias, 128, pool, impl, batch_major=False,
+                          dumps=False)
+  assert np.array_equal(s_fast, s_ref)
 
 
 def test_spiking_conv_tau_not_power_of_two_and_extremes(cuda_lib, oracle_lib):
