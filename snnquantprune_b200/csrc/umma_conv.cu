@@ -49,6 +49,8 @@ struct UmmaArgs {
   int pool;
   int base_off_mode;
   int tb_swapped;            // tensor-map dims 3/4 are (b, t) instead of (t, b)
+  int one;                   // always 1 (runtime operand of the magic-number IMAD, see epilogue.cuh)
+  int debug;                 // SNNQP_UMMA_DEBUG: bit0 skip MMA issue, bit1 skip epilogue math (timing bisection only)
   uint32_t stage_tx_bytes;
   const float *scale, *bias;
   const uint8_t *slab_nz;    // 36 flags (tap*4 + k32) or nullptr
@@ -149,6 +151,7 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               if (!((nz_mask >> (tap * 4 + k)) & 1)) continue;     // block-sparse skip of an all-zero K-slab
+              if (a.debug & 1) continue;
               const uint32_t aa = w_addr + tap * kTapBytes + k * 32;
               const uint32_t ba = x_addr + (kh * a.P + kw) * 128 + k * 32;
               const uint64_t ad = ptx::make_desc_sw128(aa, 0);
@@ -171,14 +174,16 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     const int w0 = (WCFG == 64) ? g * WC : 0;       // first column of this thread
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const int Wo = a.pool ? a.W / 2 : a.W;
-    float u[R][WC];
+    float u[R][WC];                 // generic variant
+    uint64_t u2[R][WC / 2];         // FAST variant: packed pairs (columns 2p, 2p+1)
+    const Lif2Consts k2(sc, bi, a.one);
     uint32_t step = 0;
     for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
       const int b = item / a.strips, h0 = (item % a.strips) * TH;
 #pragma unroll
       for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int j = 0; j < WC; ++j) u[r][j] = 0.0f;          // zero carry (spiking_learning.py:464-472)
+        for (int j = 0; j < WC; ++j) { u[r][j] = 0.0f; u2[r][j >> 1] = 0ull; }   // zero carry (spiking_learning.py:464-472)
       for (int t = 0; t < a.T; ++t, ++step) {
         const uint32_t s = step & 1, ph = (step >> 1) & 1;
         ptx::mbar_wait(acc_full + s, ph);
@@ -194,27 +199,25 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(acc_empty + s);        // TMEM buffer free for step + 2
 
+        if (a.debug & 2) continue;
         if constexpr (FAST) {
-          const LifParams<true> lif{2.0f, 1.0f, 0.0f};
           uint8_t *y0 = a.spikes + (int64_t)t * a.y_stride_t + (int64_t)b * a.y_stride_b + c;
-          int nspk = 0;
+          uint64_t cnt2 = 0ull;
 #pragma unroll
           for (int pr = 0; pr < R / 2; ++pr) {
             uint8_t *yrow = y0 + ((int64_t)((h0 + r0 + 2 * pr) >> 1) * Wo + (w0 >> 1)) * kC;
 #pragma unroll
             for (int pc = 0; pc < WC / 2; ++pc) {
-              bool any = false;
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int r = 2 * pr + (e >> 1), j = 2 * pc + (e & 1);
-                const bool sp = lif.step(u[r][j], __fmaf_rn((float)(int32_t)acc[r][j], sc, bi));
-                any |= sp;
-                if constexpr (COUNTS) nspk += sp ? 1 : 0;
-              }
-              yrow[pc * kC] = any ? 1 : 0;
+              const uint64_t st = lif2_std(u2[2 * pr][pc], acc[2 * pr][2 * pc], acc[2 * pr][2 * pc + 1], k2);
+              const uint64_t sb = lif2_std(u2[2 * pr + 1][pc], acc[2 * pr + 1][2 * pc], acc[2 * pr + 1][2 * pc + 1], k2);
+              yrow[pc * kC] = pool2x2(st, sb);
+              if constexpr (COUNTS) cnt2 = add2(cnt2, add2(st, sb));
             }
           }
           if constexpr (COUNTS) {
+            float ca, cb;
+            unpack2(cnt2, ca, cb);
+            const int nspk = (int)(ca + cb);
             if (nspk) atomicAdd(a.counts + ((int64_t)b * a.T + t) * kC + c, nspk);
           }
           continue;
@@ -372,8 +375,10 @@ int launch_conv3x3_umma(const snnqp_block_params &p, const uint8_t *x, const int
   a.tau = p.tau; a.v_th = p.v_threshold; a.v_reset = p.v_reset;
   a.pool = p.pool;
   a.tb_swapped = tb_swapped ? 1 : 0;
-  const char *bo = getenv("SNNQP_UMMA_BASEOFF");
-  a.base_off_mode = bo ? atoi(bo) : 0;
+  a.one = 1;
+  a.base_off_mode = 0;   // the hardware applies the 128B swizzle on absolute smem address bits (measured)
+  const char *dbg = getenv("SNNQP_UMMA_DEBUG");
+  a.debug = dbg ? atoi(dbg) : 0;
   a.stage_tx_bytes = (uint32_t)((TH + 2) * P * kC);
   a.scale = scale; a.bias = bias;
   a.slab_nz = reinterpret_cast<const uint8_t *>(wq) + kWBytes;   // blob tail written by snnqp_pack_conv3x3
