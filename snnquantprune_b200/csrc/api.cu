@@ -153,7 +153,7 @@ int snnqp_tcja_fwd(const snnqp_block_params *p, const uint8_t *spikes, const int
   if (!p || !wq_t || !wq_c || !scale_t || !scale_c || !counts || !att)
     return invalid("snnqp_tcja_fwd: null pointer");
   if (p->Cin != 128) return unsupported("snnqp_tcja_fwd: C=%d (supported: 128)", p->Cin);
-  if (p->T <= 0 || p->T > 64 || p->B <= 0 || p->H <= 0 || p->W <= 0)
+  if (p->T <= 0 || p->T > 32 || p->B <= 0 || p->H <= 0 || p->W <= 0)
     return invalid("snnqp_tcja_fwd: bad shape T=%d B=%d H=%d W=%d", p->T, p->B, p->H, p->W);
   if (p->H * p->W > (1 << 16)) return unsupported("snnqp_tcja_fwd: H*W too large");
   return launch_tcja(*p, spikes, wq_t, wq_c, scale_t, scale_c, counts, att, (cudaStream_t)stream);

@@ -341,31 +341,38 @@ k_tcja_counts(const snnqp_block_params p, const uint8_t *__restrict__ s,
 //   t_out[t',b,c] = scale_t * sum_{j<4, t} cnt[t][c+j-1] * q_t[j][t][t']   (conv over the channel axis, features = T)
 //   c_out[t,b,c'] = scale_c * sum_{j<4, c} cnt[t+j-1][c] * q_c[j][c][c']   (conv over the time axis, features = C)
 // 'SAME' pads for k=4: low 1, high 2 (reference flax_qconv.py:131-142).
-__global__ void __launch_bounds__(128)
+// One block per sample: the 4*C*C conv_c weights (64 KB) and the sample's counts are staged
+// in shared memory once and reused for all T timesteps; thread = (channel, timestep parity).
+__global__ void __launch_bounds__(256)
 k_tcja_att(const snnqp_block_params p, const int32_t *__restrict__ counts,
            const int8_t *__restrict__ wq_t, const int8_t *__restrict__ wq_c,
            const float *__restrict__ scale_t, const float *__restrict__ scale_c,
            float *__restrict__ att) {
-  // one block per (t, b), one thread per channel; the sample's counts are staged in smem
-  extern __shared__ int32_t cnt[];   // [T][C]
-  const int t = blockIdx.x, b = blockIdx.y, T = p.T, C = p.Cin;
+  extern __shared__ __align__(16) uint8_t tcja_smem[];
+  const int b = blockIdx.x, T = p.T, C = p.Cin;
+  int8_t *qc = reinterpret_cast<int8_t *>(tcja_smem);                       // [4][C][C]
+  int32_t *cnt = reinterpret_cast<int32_t *>(tcja_smem + 4 * C * C);        // [T][C]
+  int8_t *qt = reinterpret_cast<int8_t *>(cnt + T * C);                     // [4][T][T]
+  for (int d = threadIdx.x; d < 4 * C * C / 16; d += blockDim.x)
+    reinterpret_cast<int4 *>(qc)[d] = __ldg(reinterpret_cast<const int4 *>(wq_c) + d);
   for (int d = threadIdx.x; d < T * C; d += blockDim.x) cnt[d] = counts[(int64_t)b * T * C + d];
+  for (int d = threadIdx.x; d < 4 * T * T; d += blockDim.x) qt[d] = wq_t[d];
   __syncthreads();
   const float st = *scale_t, scc = *scale_c;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    int acc_t = 0, acc_c = 0;
+  const int c = threadIdx.x % C, part = threadIdx.x / C, nparts = blockDim.x / C;
+  for (int t = part; t < T; t += nparts) {
+    int acc_c = 0, acc_t = 0;
     for (int j = 0; j < 4; ++j) {
-      const int cc = c + j - 1;
-      if (cc >= 0 && cc < C)
-        for (int ti = 0; ti < T; ++ti)
-          acc_t += cnt[ti * C + cc] * (int)__ldg(wq_t + (j * T + ti) * T + t);          // warp-uniform weight
       const int tt = t + j - 1;
       if (tt >= 0 && tt < T) {
         const int32_t *row = cnt + tt * C;
-        const int8_t *wc = wq_c + (int64_t)j * C * C + c;                              // coalesced over c
+        const int8_t *wc = qc + j * C * C + c;
 #pragma unroll 8
-        for (int ci = 0; ci < C; ++ci) acc_c += row[ci] * (int)__ldg(wc + (int64_t)ci * C);
+        for (int ci = 0; ci < C; ++ci) acc_c += row[ci] * (int)wc[ci * C];
       }
+      const int cc = c + j - 1;
+      if (cc >= 0 && cc < C)
+        for (int ti = 0; ti < T; ++ti) acc_t += cnt[ti * C + cc] * (int)qt[(j * T + ti) * T + t];
     }
     const float to = __fmul_rn((float)acc_t, st);
     const float co = __fmul_rn((float)acc_c, scc);
@@ -504,8 +511,9 @@ int launch_tcja(const snnqp_block_params &p, const uint8_t *spikes, const int8_t
     k_tcja_counts<<<p.T * p.B, 256, 0, st>>>(p, spikes, counts);
     SNNQP_POST_LAUNCH("k_tcja_counts");
   }
-  const size_t smem = (size_t)p.T * p.Cin * sizeof(int32_t);
-  k_tcja_att<<<dim3(p.T, p.B), 128, smem, st>>>(p, counts, wq_t, wq_c, scale_t, scale_c, att);
+  const size_t smem = (size_t)4 * p.Cin * p.Cin + (size_t)p.T * p.Cin * sizeof(int32_t) + (size_t)4 * p.T * p.T + 16;
+  SNNQP_CUDA(cudaFuncSetAttribute(k_tcja_att, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_tcja_att<<<p.B, 256, smem, st>>>(p, counts, wq_t, wq_c, scale_t, scale_c, att);
   SNNQP_POST_LAUNCH("k_tcja_att");
   return SNNQP_OK;
 }

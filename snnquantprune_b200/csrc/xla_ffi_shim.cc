@@ -1,0 +1,76 @@
+// XLA FFI custom-call shim over the C-ABI.
+// jaxlib's FFI headers are not present in this image, so the handlers are
+// compiled only where <xla/ffi/api/ffi.h> exists; elsewhere this TU is empty.
+#if defined(__has_include)
+#if __has_include("xla/ffi/api/ffi.h")
+#define SNNQP_HAVE_XLA_FFI 1
+#endif
+#endif
+
+#ifdef SNNQP_HAVE_XLA_FFI
+#include <cuda_runtime.h>
+
+#include "snnqp.h"
+#include "xla/ffi/api/ffi.h"
+
+namespace ffi = xla::ffi;
+
+static ffi::Error Status(int rc) {
+  return rc == SNNQP_OK ? ffi::Error::Success() : ffi::Error(ffi::ErrorCode::kInvalidArgument, snnqp_last_error());
+}
+
+// SpikingBlock(QuantConv3x3, BatchNorm, multi_step_LIF) [+ max-pool]; x: (B,T,H,W,Cin) uint8, batch-major
+static ffi::Error SpikingConvImpl(cudaStream_t stream, ffi::Buffer<ffi::U8> x, ffi::Buffer<ffi::S8> wq,
+                                  ffi::Buffer<ffi::F32> scale, ffi::Buffer<ffi::F32> bias,
+                                  ffi::ResultBuffer<ffi::U8> spikes, int32_t pool, float tau, float v_th,
+                                  float v_reset) {
+  auto d = x.dimensions();
+  snnqp_block_params p{};
+  p.B = (int32_t)d[0]; p.T = (int32_t)d[1]; p.H = (int32_t)d[2]; p.W = (int32_t)d[3]; p.Cin = (int32_t)d[4];
+  p.Cout = (int32_t)scale.dimensions()[0];
+  p.x_stride_t = (int64_t)p.H * p.W * p.Cin; p.x_stride_b = p.x_stride_t * p.T;
+  const int Ho = pool ? p.H / 2 : p.H, Wo = pool ? p.W / 2 : p.W;
+  p.y_stride_t = (int64_t)Ho * Wo * p.Cout; p.y_stride_b = p.y_stride_t * p.T;
+  p.tau = tau; p.v_threshold = v_th; p.v_reset = v_reset; p.pool = pool; p.impl = SNNQP_IMPL_AUTO;
+  return Status(snnqp_spiking_conv3x3_fwd(&p, x.typed_data(), nullptr, wq.typed_data(), scale.typed_data(),
+                                          bias.typed_data(), spikes->typed_data(), nullptr, nullptr, stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(SnnqpSpikingConv, SpikingConvImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::U8>>()
+                                  .Arg<ffi::Buffer<ffi::S8>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::U8>>()
+                                  .Attr<int32_t>("pool")
+                                  .Attr<float>("tau")
+                                  .Attr<float>("v_threshold")
+                                  .Attr<float>("v_reset"));
+
+// SpikingBlock(QuantDense, multi_step_LIF); x: (B,T,K) uint8
+static ffi::Error SpikingDenseImpl(cudaStream_t stream, ffi::Buffer<ffi::U8> x, ffi::Buffer<ffi::S8> wq,
+                                   ffi::Buffer<ffi::F32> scale, ffi::Buffer<ffi::F32> bias,
+                                   ffi::ResultBuffer<ffi::U8> spikes, float tau, float v_th, float v_reset) {
+  auto d = x.dimensions();
+  snnqp_block_params p{};
+  p.B = (int32_t)d[0]; p.T = (int32_t)d[1]; p.H = p.W = 1; p.Cin = (int32_t)d[2];
+  p.Cout = (int32_t)scale.dimensions()[0];
+  p.x_stride_t = p.Cin; p.x_stride_b = (int64_t)p.T * p.Cin;
+  p.y_stride_t = p.Cout; p.y_stride_b = (int64_t)p.T * p.Cout;
+  p.tau = tau; p.v_threshold = v_th; p.v_reset = v_reset; p.impl = SNNQP_IMPL_AUTO;
+  return Status(snnqp_spiking_dense_fwd(&p, x.typed_data(), nullptr, wq.typed_data(), scale.typed_data(),
+                                        bias.typed_data(), spikes->typed_data(), nullptr, nullptr, stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(SnnqpSpikingDense, SpikingDenseImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::U8>>()
+                                  .Arg<ffi::Buffer<ffi::S8>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::U8>>()
+                                  .Attr<float>("tau")
+                                  .Attr<float>("v_threshold")
+                                  .Attr<float>("v_reset"));
+#endif  // SNNQP_HAVE_XLA_FFI
