@@ -163,6 +163,10 @@ def run_ours(args):
   from snnquantprune_b200 import CextNetEngine, pack_cextnet, synthetic, _lib
   from snnquantprune_b200 import dist as D
 
+  # libraries (NCCL) may print to stdout: keep fd 1 clean for the single JSON line
+  sys.stdout.flush()
+  saved_stdout = os.dup(1)
+  os.dup2(2, 1)
   rank, ws, local = D.init("nccl")
   torch.cuda.set_device(local)
   dev = torch.device("cuda", local)
@@ -261,8 +265,12 @@ def run_ours(args):
         "accuracy_vs_random_labels": cnt[0].item() / cnt[2].item(),
         "kernels": args.kernels,
     }
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
   D.barrier()
+  if torch.distributed.is_initialized():
+    torch.distributed.destroy_process_group()
   return 0
 
 
@@ -296,11 +304,17 @@ def dominant_kernel_roofline(eng, frames, args, dev):
   ms = e0.elapsed_time(e1) / n
   ops = CONV2_GOP_PER_SAMPLE * 1e9 * Bc * (pk.T / 20.0) * (pk.H / 128.0) ** 2
   pkp = peaks()
+  traffic = None
+  tpath = os.path.join(ROOT, "profiles", "r1_conv2_traffic.json")
+  if os.path.exists(tpath):
+    tj = json.load(open(tpath))          # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
+    if tj.get("samples_per_launch") == Bc and tj.get("T") == pk.T:
+      traffic = tj["dram_bytes_per_launch"]
   achieved = ops / (ms / 1e3) / 1e12
   peak = 2 * pkp["bf16"]
   return {"kernel": "conv2 fused block (snnqp_spiking_conv3x3_fwd, 64x64x128->128, T steps inside)",
           "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-          "traffic": None, "ms_per_launch": ms, "units_per_launch": f"{Bc} samples x T={pk.T}",
+          "traffic": traffic, "ms_per_launch": ms, "units_per_launch": f"{Bc} samples x T={pk.T}",
           "peak_source": f"2 x {pkp['src']} bf16 burst (no int8 peak is measured; nominal dense int8 is 4500 TOP/s)",
           "frac_of_nominal_int8": achieved / 4500.0}
 

@@ -15,6 +15,19 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a fully converged warp (elect.sync).  Use this -- not `lane == 0` --
+// to guard single-thread tcgen05 / TMA issue: ptxas recognises it as a uniform
+// single-lane region and keeps descriptors on the uniform datapath.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ------------------------------------------------------------- mbarrier ----
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -98,6 +111,16 @@ __device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with the A operand read from tensor memory (lanes = rows, 4 int8 per 32-bit column)
+__device__ __forceinline__ void mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // mbarrier arrives when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void mma_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -157,6 +180,12 @@ __host__ __device__ constexpr uint32_t make_idesc_i8(int M, int N, bool a_signed
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) \
       : "r"(taddr)                                                                                      \
       : "memory")
+
+#define SNNQP_TMEM_ST_X8(taddr, r)                                                                      \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"          \
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), \
+               "r"(r[7])                                                                                \
+               : "memory")
 
 // named barrier among a subset of warps (id 1..15; id 0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {

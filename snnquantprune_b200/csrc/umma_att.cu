@@ -111,7 +111,7 @@ k_conv_att_umma(const __grid_constant__ CUtensorMap tmap_w, const ConvAttArgs a)
 
   if (warp == kEpiWarps) {
     // ===================== weights TMA + MMA issuer =====================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       ptx::mbar_expect_tx(w_full, kWBytes);
       for (int tap = 0; tap < 9; ++tap) ptx::tma_load_2d(w_smem + tap * kTapBytes, &tmap_w, w_full, 0, tap * kC);
       uint64_t nz_mask = ~0ull;
@@ -348,7 +348,7 @@ k_dense_umma(const __grid_constant__ CUtensorMap tmap_w, const DenseArgs a) {
 
   if (warp == kEpiWarps) {
     // ===================== weight TMA + MMA issuer =====================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       const uint32_t idesc = ptx::make_idesc_i8(128, a.N, true, false);
       uint32_t kstep = 0, it = 0;
       for (int item = blockIdx.x; item < a.total_items; item += gridDim.x, ++it) {

@@ -37,8 +37,16 @@ constexpr int kStageBytes = 35840;              // >= (2P+2+N) rows * 128 B for 
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = (kEpiWarps + 2) * 32;  // + TMA warp + MMA warp
 constexpr int kTmemCols = 512;
-constexpr int kAccStride = 256;                 // TMEM column offset of accumulator buffer 1
-constexpr int kSmemBytes = kWBytes + 2 * kStageBytes + 1024 /*barriers*/ + 1024 /*align slack*/;
+// Weights (A operand) of the first kTmemTaps taps live in TENSOR MEMORY for the CTA's lifetime: with N = 144 an
+// SS-mode MMA pulls (128 + 144) * 32 B from shared memory per 72 cycles (94 % of the 128 B/cycle port, measured
+// tensor pipe 57 % active); reading A from TMEM leaves 64 B/cycle.  TMEM budget: 2 x 144 accumulator columns +
+// 7 taps x 4 K-steps x 8 columns = 512 exactly.  The last two taps stay in shared memory (32 KB).
+constexpr int kTmemTaps = 7, kSmemTaps = 9 - kTmemTaps;
+constexpr int kWSmemBytes = kSmemTaps * kTapBytes;   // 32768
+constexpr int kAccStride = 144;                 // TMEM column offset of accumulator buffer 1
+constexpr int kACol0 = 2 * kAccStride;          // first TMEM column of the resident weights
+constexpr int kStages = 4;                      // input ring depth (the freed shared memory)
+constexpr int kSmemBytes = kWSmemBytes + kStages * kStageBytes + 1024 /*barriers*/ + 1024 /*align slack*/;
 
 struct UmmaArgs {
   int T, B, H, W;
@@ -58,6 +66,7 @@ struct UmmaArgs {
   float *u_final;
   int32_t *acc_dump;
   int32_t *counts;           // [B][T][C] += un-pooled spike count (nullable)
+  const int8_t *wq;          // packed weights [9][128][128] (read directly for the TMEM-resident taps)
 };
 
 template <int WCFG> struct Cfg;
@@ -76,14 +85,15 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t *w_smem = smem;
-  uint8_t *stage_smem = smem + kWBytes;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kWBytes + 2 * kStageBytes);
+  uint8_t *stage_smem = smem + kWSmemBytes;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kWSmemBytes + kStages * kStageBytes);
   uint64_t *w_full = bars + 0;
-  uint64_t *in_full = bars + 1;     // [2]
-  uint64_t *in_empty = bars + 3;    // [2]
-  uint64_t *acc_full = bars + 5;    // [2]
-  uint64_t *acc_empty = bars + 7;   // [2]
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 9);
+  uint64_t *a_ready = bars + 1;                 // weights stored to TMEM by the epilogue warps
+  uint64_t *in_full = bars + 2;                 // [kStages]
+  uint64_t *in_empty = in_full + kStages;       // [kStages]
+  uint64_t *acc_full = in_empty + kStages;      // [2]
+  uint64_t *acc_empty = acc_full + 2;           // [2]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -91,9 +101,12 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     ptx::prefetch_tmap(&tmap_x);
     ptx::prefetch_tmap(&tmap_w);
     ptx::mbar_init(w_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    ptx::mbar_init(a_ready, kEpiWarps);
+    for (int i = 0; i < kStages; ++i) {
       ptx::mbar_init(in_full + i, 1);
       ptx::mbar_init(in_empty + i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(acc_full + i, 1);
       ptx::mbar_init(acc_empty + i, kEpiWarps);
     }
@@ -107,16 +120,17 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 
   if (warp == kEpiWarps) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      ptx::mbar_expect_tx(w_full, kWBytes);
-      for (int tap = 0; tap < 9; ++tap)
-        ptx::tma_load_2d(w_smem + tap * kTapBytes, &tmap_w, w_full, 0, tap * kC);
+    if (ptx::elect_one()) {
+      ptx::mbar_expect_tx(w_full, kWSmemBytes);
+      for (int tap = kTmemTaps; tap < 9; ++tap)
+        ptx::tma_load_2d(w_smem + (tap - kTmemTaps) * kTapBytes, &tmap_w, w_full, 0, tap * kC);
       uint32_t step = 0;
       for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
         const int b = item / a.strips, h0 = (item % a.strips) * TH;
         for (int t = 0; t < a.T; ++t, ++step) {
-          const uint32_t s = step & 1, ph = (step >> 1) & 1;
+          const uint32_t s = step % kStages, ph = (step / kStages) & 1;
           ptx::mbar_wait(in_empty + s, ph ^ 1);
+          if (a.debug & 4) { ptx::mbar_arrive(in_full + s); continue; }     // timing bisection: no input loads
           ptx::mbar_expect_tx(in_full + s, a.stage_tx_bytes);
           ptx::tma_load_5d(stage_smem + s * kStageBytes, &tmap_x, in_full + s, 0, -1, h0 - 1,
                            a.tb_swapped ? b : t, a.tb_swapped ? t : b);
@@ -125,7 +139,10 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     }
   } else if (warp == kEpiWarps + 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The leader is chosen with elect.sync: inside a plain `lane == 0` branch ptxas treats the region as divergent
+    // and wraps every UTCIMMA in an ELECT / BRA.U.ANY serialisation loop (~18 instructions per MMA, measured
+    // 112 cycles per 128x144x32 MMA instead of 72).
+    if (ptx::elect_one()) {
       uint64_t nz_mask = ~0ull;
       if (a.slab_nz) {
         nz_mask = 0;
@@ -134,33 +151,56 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       }
       const uint32_t idesc = ptx::make_idesc_i8(128, a.N, /*A = weights s8*/ true, /*B = inputs u8*/ false);
       const uint32_t w_addr = ptx::smem_u32(w_smem);
+      const uint64_t desc_hi = ptx::make_desc_sw128(0, 0);
+      const uint64_t ad0 = desc_hi + (w_addr >> 4);
+      uint32_t tap_off16[9];                       // (kh * P + kw) rows of 128 B, in 16-byte units
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) tap_off16[tap] = (uint32_t)(((tap / 3) * a.P + (tap % 3)) * 8);
+      const bool dense_path = ((nz_mask & 0xFFFFFFFFFull) == 0xFFFFFFFFFull) && !(a.debug & 1);
       ptx::mbar_wait(w_full, 0);
+      ptx::mbar_wait(a_ready, 0);
+      ptx::tc_fence_after();
       uint32_t step = 0;
       for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
         for (int t = 0; t < a.T; ++t, ++step) {
           const uint32_t s = step & 1, ph = (step >> 1) & 1;
+          const uint32_t si = step % kStages, phi = (step / kStages) & 1;
           ptx::mbar_wait(acc_empty + s, ph ^ 1);
-          ptx::mbar_wait(in_full + s, ph);
+          ptx::mbar_wait(in_full + si, phi);
           ptx::tc_fence_after();
-          const uint32_t x_addr = ptx::smem_u32(stage_smem + s * kStageBytes);
+          const uint32_t x_addr = ptx::smem_u32(stage_smem + si * kStageBytes);
           const uint32_t d_tmem = tmem_base + s * kAccStride;
-          uint32_t accumulate = 0;
+          // descriptors: constant high half; the 14-bit start-address field (16-byte units) is the only
+          // part that changes, and shared-memory addresses never carry out of it
+          const uint64_t bd0 = desc_hi + (x_addr >> 4);
+          if (dense_path) {
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            const int kh = tap / 3, kw = tap % 3;
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint64_t bd_tap = bd0 + tap_off16[tap];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (!((nz_mask >> (tap * 4 + k)) & 1)) continue;     // block-sparse skip of an all-zero K-slab
-              if (a.debug & 1) continue;
-              const uint32_t aa = w_addr + tap * kTapBytes + k * 32;
-              const uint32_t ba = x_addr + (kh * a.P + kw) * 128 + k * 32;
-              const uint64_t ad = ptx::make_desc_sw128(aa, 0);
-              const uint64_t bd = ptx::make_desc_sw128(ba, a.base_off_mode ? (ba >> 7) & 7 : 0);
-              ptx::mma_i8(d_tmem, ad, bd, idesc, accumulate);
+              for (int k = 0; k < 4; ++k) {
+                if (tap < kTmemTaps)
+                  ptx::mma_i8_ts(d_tmem, tmem_base + kACol0 + (tap * 4 + k) * 8, bd_tap + 2 * k, idesc, (tap | k) != 0);
+                else
+                  ptx::mma_i8(d_tmem, ad0 + ((tap - kTmemTaps) * kTapBytes + k * 32) / 16, bd_tap + 2 * k, idesc, 1);
+              }
+            }
+          } else {
+            // block-sparse path: skip the all-zero K-slabs
+            uint32_t accumulate = 0;
+#pragma unroll 1
+            for (int sl = 0; sl < 36; ++sl) {
+              if (!((nz_mask >> sl) & 1) || (a.debug & 1)) continue;
+              const int tap = sl >> 2, k = sl & 3;
+              const uint64_t bd = bd0 + tap_off16[tap] + 2 * k;
+              if (tap < kTmemTaps)
+                ptx::mma_i8_ts(d_tmem, tmem_base + kACol0 + sl * 8, bd, idesc, accumulate);
+              else
+                ptx::mma_i8(d_tmem, ad0 + ((tap - kTmemTaps) * kTapBytes + k * 32) / 16, bd, idesc, accumulate);
               accumulate = 1;
             }
           }
-          ptx::mma_commit(in_empty + s);   // input stage reusable once these MMAs have read it
+          ptx::mma_commit(in_empty + si);  // input stage reusable once these MMAs have read it
           ptx::mma_commit(acc_full + s);   // accumulator ready for the epilogue
         }
       }
@@ -174,6 +214,26 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     const int w0 = (WCFG == 64) ? g * WC : 0;       // first column of this thread
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const int Wo = a.pool ? a.W / 2 : a.W;
+    {
+      // one-time: this thread's weight row (output channel c) of the TMEM-resident taps -> tensor memory.
+      // A-operand layout: lane = row, 32-bit column j of a K-step holds K bytes 4j .. 4j+3.
+      const int tap0 = g == 0 ? 0 : 4, tap1 = g == 0 ? 4 : kTmemTaps;
+      for (int tap = tap0; tap < tap1; ++tap) {
+        const int4 *wrow = reinterpret_cast<const int4 *>(a.wq + ((int64_t)tap * kC + c) * kC);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int4 lo = __ldg(wrow + 2 * k), hi = __ldg(wrow + 2 * k + 1);
+          const uint32_t wv[8] = {(uint32_t)lo.x, (uint32_t)lo.y, (uint32_t)lo.z, (uint32_t)lo.w,
+                                  (uint32_t)hi.x, (uint32_t)hi.y, (uint32_t)hi.z, (uint32_t)hi.w};
+          const uint32_t taddr = lane_addr + kACol0 + (tap * 4 + k) * 8;
+          SNNQP_TMEM_ST_X8(taddr, wv);
+        }
+      }
+      ptx::tc_wait_st();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(a_ready);
+    }
     float u[R][WC];                 // generic variant
     uint64_t u2[R][WC / 2];         // FAST variant: packed pairs (columns 2p, 2p+1)
     const Lif2Consts k2(sc, bi, a.one);
@@ -382,7 +442,7 @@ int launch_conv3x3_umma(const snnqp_block_params &p, const uint8_t *x, const int
   a.stage_tx_bytes = (uint32_t)((TH + 2) * P * kC);
   a.scale = scale; a.bias = bias;
   a.slab_nz = reinterpret_cast<const uint8_t *>(wq) + kWBytes;   // blob tail written by snnqp_pack_conv3x3
-  a.spikes = spikes; a.u_final = u_final; a.acc_dump = acc_dump; a.counts = counts;
+  a.spikes = spikes; a.u_final = u_final; a.acc_dump = acc_dump; a.counts = counts; a.wq = wq;
 
   const int grid = a.total_items < sm_count() ? a.total_items : sm_count();
   const bool fast = p.tau == 2.0f && p.v_threshold == 1.0f && p.v_reset == 0.0f && p.pool && !u_final && !acc_dump;

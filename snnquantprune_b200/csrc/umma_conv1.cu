@@ -102,7 +102,7 @@ k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
 
   if (warp == kEpiWarps) {
     // ===================== TMA producer: 4 input rows x 144 B per step =====================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       uint32_t step = 0;
       for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
         const int tile = item % a.tiles_per_row, qh = (item / a.tiles_per_row) % QH;
@@ -124,7 +124,7 @@ k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
     }
   } else if (warp == kEpiWarps + 1) {
     // ===================== MMA issuer: 4 x (128 x 32 x 32) per step =====================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       const uint32_t idesc = ptx::make_idesc_i8(128, kQuadsPerTile, true, false);
       const uint32_t w_addr = ptx::smem_u32(w_smem), b_addr = ptx::smem_u32(b_smem);
       uint32_t step = 0;
