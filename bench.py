@@ -327,7 +327,7 @@ def main():
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
   ap.add_argument("--kernels", default="auto", choices=["auto", "simt", "tcgen05"])
   ap.add_argument("--batch", type=int, default=512, help="samples per GPU per step")
-  ap.add_argument("--chunk", type=int, default=16, help="samples per fused launch (keeps activations in L2)")
+  ap.add_argument("--chunk", type=int, default=256, help="samples per head launch (large: exact CTA waves; L2 residency measured irrelevant)")
   ap.add_argument("--bits", type=int, default=8)
   ap.add_argument("--prune", type=float, default=0.5)
   ap.add_argument("--T", type=int, default=20)
