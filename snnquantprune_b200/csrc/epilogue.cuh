@@ -29,6 +29,16 @@ struct LifParams {
   }
 };
 
+// int32 accumulator -> fp32 on the FMA pipe: as_float(acc * one + 0x4B400000) - 1.5 * 2^23 (IMAD + FADD), exact
+// for |acc| < 2^22.  `one` is a runtime 1 so that ptxas keeps the IMAD instead of folding it to an ALU-pipe
+// IADD3.  ncu: with I2FP the half-rate ALU pipe (I2FP + FSETP + FSEL) is the epilogue's bottleneck (79 % busy
+// vs 29 % for the FMA pipe); this moves 2 of its ~7.5 cycles per neuron over.
+__device__ __forceinline__ float cvt_acc_fma_pipe(uint32_t acc, int one) {
+  uint32_t m;
+  asm("mad.lo.s32 %0, %1, %2, 0x4B400000;" : "=r"(m) : "r"(acc), "r"(one));
+  return __fadd_rn(__uint_as_float(m), -12582912.0f);
+}
+
 __device__ __forceinline__ bool lif_is_std(float tau, float v_th, float v_reset) {
   return tau == 2.0f && v_th == 1.0f && v_reset == 0.0f;
 }

@@ -181,7 +181,13 @@ __host__ __device__ constexpr uint32_t make_idesc_i8(int M, int N, bool a_signed
       : "r"(taddr)                                                                                      \
       : "memory")
 
-#define SNNQP_TMEM_ST_X8(taddr, r)                                                                      \
+#define SNNQP_TMEM_LD_X4(taddr, r)                                                                      \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"                          \
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])                                         \
+               : "r"(taddr)                                                                             \
+               : "memory")
+
+#define SNNQP_TMEM_ST_X8(taddr, r)                                                                    \
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"          \
                ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), \
                "r"(r[7])                                                                                \

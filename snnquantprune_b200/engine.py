@@ -132,11 +132,19 @@ class CextNetEngine:
     # head: conv1 -> conv2 -> conv3, chunk by chunk
     for b0 in range(0, B, Bc):
       n = min(Bc, B - b0)
-      s1, s2 = ws["s1"][:n], ws["s2"][:n]
-      self._conv(0, frames[b0:b0 + n], s1, n, H, 2, 1, collect=collect, key="conv1")
-      self._conv(1, s1, s2, n, H // 2, C, 1, collect=collect, key="conv2")
-      self._conv(2, s2, ws["s3"][b0:b0 + n], n, H // 4, C, 1, collect=collect, key="conv3")
+      self._head(frames[b0:b0 + n], b0, n, ws, collect)
+    self._tail(B, ws, logits, collect)
 
+  def _head(self, frames_chunk, b0, n, ws, collect=None):
+    H, C = self.pk.H, self.pk.channels
+    s1, s2 = ws["s1"][:n], ws["s2"][:n]
+    self._conv(0, frames_chunk, s1, n, H, 2, 1, collect=collect, key="conv1")
+    self._conv(1, s1, s2, n, H // 2, C, 1, collect=collect, key="conv2")
+    self._conv(2, s2, ws["s3"][b0:b0 + n], n, H // 4, C, 1, collect=collect, key="conv3")
+
+  def _tail(self, B, ws, logits, collect=None):
+    pk = self.pk
+    H, C, T = pk.H, pk.channels, pk.T
     if collect is None:
       # tail, fused: pooled spikes + spike counts straight from the conv epilogues
       ws["cnt4"].zero_(); ws["cnt5"].zero_()
@@ -184,6 +192,47 @@ class CextNetEngine:
       raise ValueError("collect= needs B <= chunk")
     logits = torch.empty((B, self.pk.num_classes), device=self.device, dtype=torch.float32)
     self._run(frames, logits, collect)
+    return logits
+
+  def forward_host(self, host_frames: torch.Tensor, out_host: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """End-to-end call from HOST memory: ``host_frames`` is a (pinned) uint8 CPU tensor
+    (B,T,H,W,2).  Chunks are copied host->device on a side stream into two staging buffers
+    while the previous chunk's conv1-3 run, so the PCIe transfer overlaps compute.  Returns
+    the logits on the device, or copies them into ``out_host`` (pinned) if given."""
+    if host_frames.is_cuda or host_frames.dtype != torch.uint8:
+      raise ValueError("forward_host takes a uint8 CPU (pinned) tensor; use forward() for device tensors")
+    pk = self.pk
+    if tuple(host_frames.shape[1:]) != (pk.T, pk.H, pk.H, 2):
+      raise ValueError(f"frames shape {tuple(host_frames.shape)} != (B,{pk.T},{pk.H},{pk.H},2)")
+    B = host_frames.shape[0]
+    Bc = min(self.chunk, B)
+    ws = self._workspace(B, Bc)
+    if "stage" not in ws:
+      ws["stage"] = torch.empty((2, Bc) + tuple(host_frames.shape[1:]), device=self.device, dtype=torch.uint8)
+    if not hasattr(self, "_copy_stream"):
+      self._copy_stream = torch.cuda.Stream(device=self.device)
+    cur = torch.cuda.current_stream(self.device)
+    logits = torch.empty((B, pk.num_classes), device=self.device, dtype=torch.float32)
+    self._copy_stream.wait_stream(cur)
+    done = []
+    for i, b0 in enumerate(range(0, B, Bc)):
+      n = min(Bc, B - b0)
+      buf = ws["stage"][i & 1][:n]
+      if i >= 2:
+        self._copy_stream.wait_event(done[i - 2])       # staging buffer free again
+      with torch.cuda.stream(self._copy_stream):
+        buf.copy_(host_frames[b0:b0 + n], non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record(self._copy_stream)
+      cur.wait_event(ready)
+      self._head(buf, b0, n, ws)
+      ev = torch.cuda.Event()
+      ev.record(cur)
+      done.append(ev)
+    self._tail(B, ws, logits)
+    if out_host is not None:
+      out_host.copy_(logits, non_blocking=True)
+      return out_host
     return logits
 
   def forward_graph(self, frames: torch.Tensor) -> torch.Tensor:

@@ -251,6 +251,36 @@ def test_spiking_conv_binary_bit_exact(cuda_lib, oracle_lib, impl, shape, bits, 
   assert np.array_equal(s_fast, s_ref)
 
 
+@pytest.mark.parametrize("impl", impls())
+@pytest.mark.parametrize("keep", [0.5, 0.1, 0.0])
+def test_block_sparse_slab_skip(cuda_lib, oracle_lib, impl, keep):
+  """north_star item 4: weight K-slabs (tap x 32 input channels x all outputs) zeroed by a
+  block-structured mask are skipped by the MMA issuer.  Unstructured magnitude masks never
+  produce such slabs, so the path is exercised with structured masks:
+  50 % / 90 % / 100 % of the 36 slabs removed (the last one = a fully pruned layer)."""
+  rng = np.random.default_rng(int(keep * 100) + 3)
+  T, B, H = 3, 2, 16
+  lay, _, bn, stt = make_layer(rng, 128, 128, 8, 0.3)
+  slab_keep = rng.uniform(size=36) < keep
+  mask = lay["prune_0"]["mask"].reshape(9, 4, 32, 128).copy()
+  mask[~slab_keep.reshape(9, 4)] = 0
+  lay["prune_0"]["mask"] = mask.reshape(3, 3, 128, 128)
+  a = lay["DuQ_0"]["a"][0]
+  q = ref_int.duq_levels_c(lay["kernel"], lay["prune_0"]["mask"], a, 8)
+  packed = pk_mod.pack_conv3x3(lay, 8, DEV, bn, stt)
+  nz = packed.slab_nz.cpu().numpy().astype(bool)
+  assert np.array_equal(nz, (q.reshape(9, 4, 32, 128) != 0).any(axis=(2, 3)).reshape(-1))
+  assert nz.sum() <= slab_keep.sum() and (keep > 0 or nz.sum() == 0)
+  x = (rng.uniform(size=(T, B, H, H, 128)) < 0.3).astype(np.uint8)
+  scale, bias = ref_int.fold_affine(lay["DuQ_0"]["c"], 8, bn, stt, 128)
+  s_ref, info = ref_int.spiking_conv3x3(x, q, scale, bias, pool=True, want=True)
+  s, u, acc = run_conv(cuda_lib, x, packed.wq, packed.scale, packed.bias, 128, True, impl, batch_major=True)
+  assert np.array_equal(acc, info["acc"]) and np.array_equal(s, s_ref) and np.array_equal(u, info["u"])
+  s_fast, _, _ = run_conv(cuda_lib, x, packed.wq, packed.scale, packed.bias, 128, True, impl, batch_major=True,
+                          dumps=False)
+  assert np.array_equal(s_fast, s_ref)
+
+
 def test_spiking_conv_tau_not_power_of_two_and_extremes(cuda_lib, oracle_lib):
   rng = np.random.default_rng(77)
   lay, q, bn, stt = make_layer(rng, 128, 128, 8, 0.5)
@@ -497,6 +527,29 @@ def test_network_layerwise_teacher_forced_and_float_path(cuda_lib, oracle_lib):
   assert np.max(np.abs(logits - lf)) <= 1e-2
 
 
+def test_config3_T10_ten_classes(cuda_lib, oracle_lib):
+  """BASELINE.json configs[3]: the spikingjelly-input variant -- same graph with T=10 and 10
+  classes (dense2 -> 100 outputs, TCJA conv_t features = 10), 8-bit weights."""
+  from snnquantprune_b200 import CextNetEngine, pack_cextnet
+  bits, T, H, B, ncls = 8, 10, 64, 2, 10
+  v = synthetic.make_variables(bits=bits, prune_percentage=0.5, T=T, H=H, num_classes=ncls, seed=41)
+  fr = synthetic.make_frames(B, T, H, H, seed=42)
+  eng = CextNetEngine(pack_cextnet(v, bits, T, H, num_classes=ncls, device=DEV))
+  c = {}
+  logits = eng.forward(dev(fr), collect=c).cpu().numpy()
+  assert logits.shape == (B, ncls)
+  tb = lambda k: np.ascontiguousarray(np.swapaxes(c[k].cpu().numpy(), 0, 1))
+  forced = {"att4": tb("att4"), "s5": tb("s5"), "att5": tb("att5"), "d1": tb("d1")}
+  co = {}
+  lo = ref_net.forward(ref_net.pack_network(v, bits, H), fr, collect=co, forced=forced)
+  for k in ("s1", "s2", "s3", "s4"):
+    assert np.array_equal(tb(k), co[k]), k
+  assert np.array_equal(tb("d2"), co["d2"]) and np.array_equal(logits, lo)
+  lf = ref_snn.cextnet_forward(v, fr, bits)
+  assert np.max(np.abs(logits - lf)) <= 1e-2
+  assert np.array_equal(eng.forward(dev(fr)).cpu().numpy(), logits)      # production path, same logits
+
+
 def test_fused_tail_equals_instrumented_tail(cuda_lib):
   """The production forward (pooled spikes + spike counts fused into the conv
   epilogues, no un-pooled tensors) must give exactly the logits of the
@@ -508,6 +561,12 @@ def test_fused_tail_equals_instrumented_tail(cuda_lib):
   l_fused = eng.forward(frd).cpu().numpy()
   l_inst = eng.forward(frd, collect={}).cpu().numpy()
   assert np.array_equal(l_fused, l_inst)
+  host = torch.from_numpy(synthetic.make_frames(B, T, H, H, seed=4)).pin_memory()
+  out_host = torch.empty((B, 11), dtype=torch.float32).pin_memory()
+  eng2 = engine_for(v, bits, T, H, chunk=2)                   # 2 chunks: exercises the double-buffered H2D path
+  eng2.forward_host(host, out_host); eng2.forward_host(host, out_host)
+  torch.cuda.synchronize()
+  assert np.array_equal(out_host.numpy(), l_fused)
   l_graph = eng.forward_graph(frd).cpu().numpy()
   l_graph2 = eng.forward_graph(frd).cpu().numpy()
   assert np.array_equal(l_graph, l_fused) and np.array_equal(l_graph2, l_fused)
