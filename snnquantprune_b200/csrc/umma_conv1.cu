@@ -61,6 +61,39 @@ __device__ __forceinline__ uint32_t sw128_off(int row, int chunk) {
   return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
 }
 
+// The contraction runs as kind::f16 (fp16 operands, fp32 accumulate in TMEM): event counts (<= 255) and
+// int8 weights are exact in fp16, every product and partial sum is an integer < 2^24, so the fp32
+// accumulator is EXACTLY the int32 accumulator -- and the epilogue needs no int->float conversion (I2FP
+// was a third of the instructions on the ALU pipe that bounds this layer).  The MMA rate halves, which is
+// irrelevant here (tensor pipe ~4 % busy).
+// bytes (2*pair, 2*pair+1) of w as unsigned -> packed fp16x2, via the 0x6400 | x = 1024 + x encoding
+__device__ __forceinline__ uint32_t u8x2_to_h2(uint32_t w, int pair) {
+  const uint32_t m = __byte_perm(w, 0x64646464u, pair ? 0x4342 : 0x4140);     // {1024 + b_lo, 1024 + b_hi}
+  uint32_t r;
+  asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(m), "r"(0x64006400u));
+  return r;
+}
+// same for signed bytes: (b ^ 0x80) = b + 128 as unsigned, then subtract 1024 + 128
+__device__ __forceinline__ uint32_t s8x2_to_h2(uint32_t w, int pair) {
+  const uint32_t m = __byte_perm(w ^ 0x80808080u, 0x64646464u, pair ? 0x4342 : 0x4140);
+  uint32_t r;
+  asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(m), "r"(0x64806480u));
+  return r;
+}
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// instruction descriptor for kind::f16: D = F32, A = B = F16, K-major
+__device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // FAST: standard LIF constants (tau 2, threshold 1, reset 0), pooled output, no
 // instrumentation outputs -- the production variant; !FAST handles everything else.
 template <bool FAST>
@@ -83,7 +116,11 @@ k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
   for (int i = threadIdx.x; i < 4 * kC * 2; i += kThreads) {
     const int j = i / (kC * 2), row = (i >> 1) % kC, half = i & 1;
     const int4 v = *reinterpret_cast<const int4 *>(a.wq4 + ((int64_t)j * kC + row) * 32 + half * 16);
-    *reinterpret_cast<int4 *>(w_smem + j * kWjBytes + sw128_off(row, half)) = v;
+    // 16 int8 weights -> 16 fp16 (exact): two 16-byte chunks of the 64-byte operand row
+    *reinterpret_cast<int4 *>(w_smem + j * kWjBytes + sw128_off(row, 2 * half)) =
+        make_int4((int)s8x2_to_h2(v.x, 0), (int)s8x2_to_h2(v.x, 1), (int)s8x2_to_h2(v.y, 0), (int)s8x2_to_h2(v.y, 1));
+    *reinterpret_cast<int4 *>(w_smem + j * kWjBytes + sw128_off(row, 2 * half + 1)) =
+        make_int4((int)s8x2_to_h2(v.z, 0), (int)s8x2_to_h2(v.z, 1), (int)s8x2_to_h2(v.w, 0), (int)s8x2_to_h2(v.w, 1));
   }
   ptx::fence_proxy_async();
   if (warp == kEpiWarps && lane == 0) {
@@ -125,7 +162,7 @@ k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
   } else if (warp == kEpiWarps + 1) {
     // ===================== MMA issuer: 4 x (128 x 32 x 32) per step =====================
     if (ptx::elect_one()) {
-      const uint32_t idesc = ptx::make_idesc_i8(128, kQuadsPerTile, true, false);
+      const uint32_t idesc = make_idesc_f16(128, kQuadsPerTile);
       const uint32_t w_addr = ptx::smem_u32(w_smem), b_addr = ptx::smem_u32(b_smem);
       uint32_t step = 0;
       for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
@@ -137,9 +174,12 @@ k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
           const uint64_t bd = ptx::make_desc_sw128(b_addr + s * kBBytes, 0);
           if (!(a.debug & 1)) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              ptx::mma_i8(tmem_base + s * kAccStride + j * kQuadsPerTile,
-                          ptx::make_desc_sw128(w_addr + j * kWjBytes, 0), bd, idesc, 0);
+            for (int j = 0; j < 4; ++j) {
+              // K = 32 fp16 = two K-steps of 16 elements (32 bytes each) inside the 128-byte swizzled row
+              const uint64_t ad = ptx::make_desc_sw128(w_addr + j * kWjBytes, 0);
+              mma_f16(tmem_base + s * kAccStride + j * kQuadsPerTile, ad, bd, idesc, 0);
+              mma_f16(tmem_base + s * kAccStride + j * kQuadsPerTile, ad + 2, bd + 2, idesc, 1);
+            }
           }
           ptx::mma_commit(b_empty + s);
           ptx::mma_commit(acc_full + s);
@@ -165,7 +205,11 @@ k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
         v.y = (int)__byte_perm(src[1], src[2], 0x5432);
         v.z = (int)__byte_perm(src2[0], src2[1], 0x5432);
         v.w = (int)__byte_perm(src2[1], src2[2], 0x5432);
-        *reinterpret_cast<int4 *>(b_smem + bs * kBBytes + sw128_off(quad, half)) = v;
+        // 16 count bytes -> 16 fp16 values (exact): two 16-byte chunks of this quad's 64-byte operand row
+        *reinterpret_cast<int4 *>(b_smem + bs * kBBytes + sw128_off(quad, 2 * half)) =
+            make_int4((int)u8x2_to_h2(v.x, 0), (int)u8x2_to_h2(v.x, 1), (int)u8x2_to_h2(v.y, 0), (int)u8x2_to_h2(v.y, 1));
+        *reinterpret_cast<int4 *>(b_smem + bs * kBBytes + sw128_off(quad, 2 * half + 1)) =
+            make_int4((int)u8x2_to_h2(v.z, 0), (int)u8x2_to_h2(v.z, 1), (int)u8x2_to_h2(v.w, 0), (int)u8x2_to_h2(v.w, 1));
         ptx::fence_proxy_async();          // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) {
@@ -215,7 +259,7 @@ k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
             bool any = false;
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              any |= lif.step(u[j][i], __fmaf_rn((float)(int32_t)acc[j][i], sc, bi));
+              any |= lif.step(u[j][i], __fmaf_rn(__uint_as_float(acc[j][i]), sc, bi));
             yrow[i * kC] = any ? 1 : 0;
           }
           continue;
@@ -227,7 +271,7 @@ k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
           m[j] = 0;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const bool sp = lif.step(u[j][i], __fmaf_rn((float)(int32_t)acc[j][i], sc, bi));
+            const bool sp = lif.step(u[j][i], __fmaf_rn(__uint_as_float(acc[j][i]), sc, bi));
             m[j] |= (sp ? 1u : 0u) << i;
           }
         }
@@ -248,7 +292,7 @@ k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
 #pragma unroll
             for (int i = 0; i < 16; ++i)
               a.acc_dump[((((int64_t)t * a.B + b) * a.H + 2 * qh + (j >> 1)) * a.W + 2 * (qw0 + i) + (j & 1)) * kC + c] =
-                  (int32_t)acc[j][i];
+                  __float2int_rn(__uint_as_float(acc[j][i]));
         }
       }
       if (a.u_final) {
