@@ -46,6 +46,10 @@ constexpr int kWSmemBytes = kSmemTaps * kTapBytes;   // 32768
 constexpr int kAccStride = 144;                 // TMEM column offset of accumulator buffer 1
 constexpr int kACol0 = 2 * kAccStride;          // first TMEM column of the resident weights
 constexpr int kStages = 4;                      // input ring depth (the freed shared memory)
+// Fast-epilogue flavour.  The packed f32x2 form converts with the magic-number trick, exact only for
+// |acc| < 2^22 ({0,1} inputs); the scalar form (I2FP) is exact for any uint8 input.  This kernel is bound by
+// the tensor pipe (97 % active), so the always-exact scalar form is the default.
+constexpr bool kPackedMath = false;
 constexpr int kSmemBytes = kWSmemBytes + kStages * kStageBytes + 1024 /*barriers*/ + 1024 /*align slack*/;
 
 struct UmmaArgs {
@@ -262,22 +266,48 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         if (a.debug & 2) continue;
         if constexpr (FAST) {
           uint8_t *y0 = a.spikes + (int64_t)t * a.y_stride_t + (int64_t)b * a.y_stride_b + c;
-          uint64_t cnt2 = 0ull;
+          if constexpr (kPackedMath) {
+            // packed f32x2 variant (magic-number conversion: exact only for |acc| < 2^22, i.e. {0,1} inputs)
+            uint64_t cnt2 = 0ull;
+#pragma unroll
+            for (int pr = 0; pr < R / 2; ++pr) {
+              uint8_t *yrow = y0 + ((int64_t)((h0 + r0 + 2 * pr) >> 1) * Wo + (w0 >> 1)) * kC;
+#pragma unroll
+              for (int pc = 0; pc < WC / 2; ++pc) {
+                const uint64_t st = lif2_std(u2[2 * pr][pc], acc[2 * pr][2 * pc], acc[2 * pr][2 * pc + 1], k2);
+                const uint64_t sb = lif2_std(u2[2 * pr + 1][pc], acc[2 * pr + 1][2 * pc], acc[2 * pr + 1][2 * pc + 1], k2);
+                yrow[pc * kC] = pool2x2(st, sb);
+                if constexpr (COUNTS) cnt2 = add2(cnt2, add2(st, sb));
+              }
+            }
+            if constexpr (COUNTS) {
+              float ca, cb;
+              unpack2(cnt2, ca, cb);
+              const int nspk = (int)(ca + cb);
+              if (nspk) atomicAdd(a.counts + ((int64_t)b * a.T + t) * kC + c, nspk);
+            }
+            continue;
+          }
+          // scalar variant: I2FP conversion, exact for every int32 accumulator (any uint8 input)
+          const LifParams<true> lifs{2.0f, 1.0f, 0.0f};
+          int nspk = 0;
 #pragma unroll
           for (int pr = 0; pr < R / 2; ++pr) {
             uint8_t *yrow = y0 + ((int64_t)((h0 + r0 + 2 * pr) >> 1) * Wo + (w0 >> 1)) * kC;
 #pragma unroll
             for (int pc = 0; pc < WC / 2; ++pc) {
-              const uint64_t st = lif2_std(u2[2 * pr][pc], acc[2 * pr][2 * pc], acc[2 * pr][2 * pc + 1], k2);
-              const uint64_t sb = lif2_std(u2[2 * pr + 1][pc], acc[2 * pr + 1][2 * pc], acc[2 * pr + 1][2 * pc + 1], k2);
-              yrow[pc * kC] = pool2x2(st, sb);
-              if constexpr (COUNTS) cnt2 = add2(cnt2, add2(st, sb));
+              bool any = false;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int r = 2 * pr + (e >> 1), j = 2 * pc + (e & 1);
+                const bool sp = lifs.step(u[r][j], __fmaf_rn((float)(int32_t)acc[r][j], sc, bi));
+                any |= sp;
+                if constexpr (COUNTS) nspk += sp ? 1 : 0;
+              }
+              yrow[pc * kC] = any ? 1 : 0;
             }
           }
           if constexpr (COUNTS) {
-            float ca, cb;
-            unpack2(cnt2, ca, cb);
-            const int nspk = (int)(ca + cb);
             if (nspk) atomicAdd(a.counts + ((int64_t)b * a.T + t) * kC + c, nspk);
           }
           continue;
