@@ -122,6 +122,8 @@ k_conv_att_umma(const __grid_constant__ CUtensorMap tmap_w, const ConvAttArgs a)
       }
       const uint32_t idesc = ptx::make_idesc_i8(128, N, true, false);
       const uint32_t w_addr = ptx::smem_u32(w_smem);
+      const uint64_t desc_hi = ptx::make_desc_sw128(0, 0);
+      const bool dense_path = (nz_mask & 0xFFFFFFFFFull) == 0xFFFFFFFFFull;
       ptx::mbar_wait(w_full, 0);
       uint32_t step = 0;
       for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
@@ -131,19 +133,27 @@ k_conv_att_umma(const __grid_constant__ CUtensorMap tmap_w, const ConvAttArgs a)
           ptx::mbar_wait(in_full + s, ph);
           ptx::tc_fence_after();
           const uint32_t x_addr = ptx::smem_u32(stage_smem + s * kStageBytes);
+          // descriptors: constant high half + 14-bit start address in 16-byte units (never carries out)
+          const uint64_t ad0 = desc_hi + (w_addr >> 4);
 #pragma unroll 1
           for (int pl = 0; pl < 3; ++pl) {
             const uint32_t d_tmem = tmem_base + s * kAccStride + pl * N;
-            uint32_t accumulate = 0;
+            const uint64_t bd0 = desc_hi + ((x_addr + pl * kPlaneBytes) >> 4);
+            if (dense_path) {
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-              const int kh = tap / 3, kw = tap % 3;
+              for (int tap = 0; tap < 9; ++tap)
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                if (!((nz_mask >> (tap * 4 + k)) & 1)) continue;
-                const uint32_t aa = w_addr + tap * kTapBytes + k * 32;
-                const uint32_t ba = x_addr + pl * kPlaneBytes + (kh * P + kw) * 128 + k * 32;
-                ptx::mma_i8(d_tmem, ptx::make_desc_sw128(aa, 0), ptx::make_desc_sw128(ba, 0), idesc, accumulate);
+                for (int k = 0; k < 4; ++k)
+                  ptx::mma_i8(d_tmem, ad0 + (tap * kTapBytes + k * 32) / 16,
+                              bd0 + (((tap / 3) * P + (tap % 3)) * 128 + k * 32) / 16, idesc, (tap | k) != 0);
+            } else {
+              uint32_t accumulate = 0;
+#pragma unroll 1
+              for (int sl = 0; sl < 36; ++sl) {
+                if (!((nz_mask >> sl) & 1)) continue;      // block-sparse skip of an all-zero K-slab
+                const int tap = sl >> 2, k = sl & 3;
+                ptx::mma_i8(d_tmem, ad0 + (tap * kTapBytes + k * 32) / 16,
+                            bd0 + (((tap / 3) * P + (tap % 3)) * 128 + k * 32) / 16, idesc, accumulate);
                 accumulate = 1;
               }
             }
@@ -351,14 +361,23 @@ k_dense_umma(const __grid_constant__ CUtensorMap tmap_w, const DenseArgs a) {
     if (ptx::elect_one()) {
       const uint32_t idesc = ptx::make_idesc_i8(128, a.N, true, false);
       uint32_t kstep = 0, it = 0;
+      const int my_items = (int)blockIdx.x < a.total_items
+                               ? (a.total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+      const uint32_t total_steps = (uint32_t)my_items * (uint32_t)kblocks;
+      // weight tile of global step g (item-major, K-block minor); issued one step ahead of the MMAs so that
+      // the TMA latency overlaps the previous K-block's MMAs
+      auto issue_load = [&](uint32_t g) {
+        const uint32_t s = g & 1, ph = (g >> 1) & 1;
+        const int item = (int)blockIdx.x + (int)(g / kblocks) * (int)gridDim.x;
+        ptx::mbar_wait(ab_empty + s, ph ^ 1);
+        ptx::mbar_expect_tx(a_full + s, kABytes);
+        ptx::tma_load_2d(a_smem + s * kABytes, &tmap_w, a_full + s, (int)(g % kblocks) * 128, (item % a.m_tiles) * 128);
+      };
+      if (total_steps) issue_load(0);
       for (int item = blockIdx.x; item < a.total_items; item += gridDim.x, ++it) {
-        const int mt = item % a.m_tiles;
-        // prologue: first weight block of this item
         for (int kb = 0; kb < kblocks; ++kb, ++kstep) {
           const uint32_t s = kstep & 1, ph = (kstep >> 1) & 1;
-          ptx::mbar_wait(ab_empty + s, ph ^ 1);
-          ptx::mbar_expect_tx(a_full + s, kABytes);
-          ptx::tma_load_2d(a_smem + s * kABytes, &tmap_w, a_full + s, kb * 128, mt * 128);
+          if (kstep + 1 < total_steps) issue_load(kstep + 1);
           if (kb == 0) ptx::mbar_wait(acc_empty, (it & 1) ^ 1);
           ptx::mbar_wait(a_full + s, ph);
           ptx::mbar_wait(b_full + s, ph);
@@ -402,14 +421,26 @@ k_dense_umma(const __grid_constant__ CUtensorMap tmap_w, const DenseArgs a) {
       }
       for (int kb = 0; kb < kblocks; ++kb, ++kstep) {
         const uint32_t s = kstep & 1, ph = (kstep >> 1) & 1;
+        // all of this thread's global loads are issued first (and before the stage barrier), so their
+        // latency overlaps the MMAs of the previous K-blocks instead of being paid one chunk at a time
+        constexpr int kMaxCh = (kMaxN * 8 + kExpWarps * 32 - 1) / (kExpWarps * 32);
+        int4 svs[kMaxCh];
+#pragma unroll
+        for (int i = 0; i < kMaxCh; ++i) {
+          const int ch = et + i * kExpWarps * 32;
+          const int row = row0 + (ch >> 3);
+          svs[i] = make_int4(0, 0, 0, 0);
+          if (ch < a.N * 8 && row < rows_total)
+            svs[i] = __ldg(reinterpret_cast<const int4 *>(a.x + (int64_t)row * a.K + kb * 128 + (ch & 7) * 16));
+        }
         ptx::mbar_wait(ab_empty + s, ph ^ 1);
         uint8_t *dst = b_smem + s * PLANES * kBPlane;
-        for (int ch = et; ch < a.N * 8; ch += kExpWarps * 32) {
+#pragma unroll
+        for (int i = 0; i < kMaxCh; ++i) {
+          const int ch = et + i * kExpWarps * 32;
+          if (ch >= a.N * 8) break;
           const int r = ch >> 3, c16 = ch & 7;
-          const int row = row0 + r;
-          int4 sv = make_int4(0, 0, 0, 0);
-          if (row < rows_total)
-            sv = __ldg(reinterpret_cast<const int4 *>(a.x + (int64_t)row * a.K + kb * 128 + c16 * 16));
+          const int4 sv = svs[i];
           const uint32_t off = (uint32_t)(r * 128 + ((c16 ^ (r & 7)) << 4));
           if (PLANES == 1) {
             *reinterpret_cast<int4 *>(dst + off) = sv;
