@@ -225,7 +225,9 @@ k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
     const float sc = a.scale[c], bi = a.bias[c];
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const int Wo = a.pool ? a.W / 2 : a.W;
-    float u[4][16];
+    float u[4][16];                  // generic variant
+    uint64_t u2[4][8];               // FAST variant: packed pairs (quads 2p, 2p+1) per quad position j
+    const Lif2Consts k2(sc, bi, 1);
     uint32_t step = 0;
     for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
       const int tile = item % a.tiles_per_row, qh = (item / a.tiles_per_row) % QH;
@@ -234,7 +236,7 @@ k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
 #pragma unroll
       for (int j = 0; j < 4; ++j)
 #pragma unroll
-        for (int i = 0; i < 16; ++i) u[j][i] = 0.0f;
+        for (int i = 0; i < 16; ++i) { u[j][i] = 0.0f; u2[j][i >> 1] = 0ull; }
       for (int t = 0; t < a.T; ++t, ++step) {
         const uint32_t s = step & 1, ph = (step >> 1) & 1;
         ptx::mbar_wait(acc_full + s, ph);
@@ -252,15 +254,19 @@ k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
 
         uint8_t *yb = a.spikes + (int64_t)t * a.y_stride_t + (int64_t)b * a.y_stride_b + c;
         if constexpr (FAST) {
-          const LifParams<true> lif{2.0f, 1.0f, 0.0f};
+          // Packed f32x2 LIF (FFMA2 / FADD2): ncu shows this kernel issue-bound (74.6 % issue slots, 6.5
+          // instructions per neuron); pairing neurons (i, i+1) of the same quad position j -- adjacent registers
+          // of one tcgen05.ld, so the pack is free -- brings it to ~4.1.  The fp32 accumulator needs no conversion.
           uint8_t *yrow = yb + ((int64_t)qh * Wo + qw0) * kC;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            bool any = false;
+          for (int p = 0; p < 8; ++p) {
+            uint64_t ssum = lif2_std_f32(u2[0][p], acc[0][2 * p], acc[0][2 * p + 1], k2);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              any |= lif.step(u[j][i], __fmaf_rn(__uint_as_float(acc[j][i]), sc, bi));
-            yrow[i * kC] = any ? 1 : 0;
+            for (int j = 1; j < 4; ++j) ssum = add2(ssum, lif2_std_f32(u2[j][p], acc[j][2 * p], acc[j][2 * p + 1], k2));
+            float sa, sb;
+            unpack2(ssum, sa, sb);                       // number of spikes in quad 2p / 2p+1
+            yrow[(2 * p) * kC] = sa != 0.0f ? 1 : 0;
+            yrow[(2 * p + 1) * kC] = sb != 0.0f ? 1 : 0;
           }
           continue;
         }
