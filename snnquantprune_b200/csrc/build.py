@@ -17,6 +17,8 @@ HEADERS = ["common.cuh", "ptx.cuh", os.path.join(ROOT, "include", "snnqp.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+if os.environ.get("SNNQP_BISECT"):          # debug-only bisection switches inside the hot loops (tools/)
+  FLAGS.append("-DSNNQP_C1_BISECT")
 
 
 def _stale() -> bool:

@@ -79,6 +79,13 @@ __device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
   return d;
 }
 
+// 1.0f if x >= 1 else 0.0f: one FSET.BF (the only ALU-pipe instruction of a neuron update)
+__device__ __forceinline__ float fset_ge1(float x) {
+  float d;
+  asm("set.ge.f32.f32 %0, %1, 0f3F800000;" : "=f"(d) : "f"(x));
+  return d;
+}
+
 struct Lif2Consts {
   uint64_t sc2, bi2, half2, nmagic2;
   int one;      // runtime 1: keeps the magic-number add an IMAD (FMA pipe) instead of an ALU-pipe IADD3

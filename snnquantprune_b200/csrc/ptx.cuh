@@ -61,6 +61,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   }
 }
 
+// Same with a nanosleep back-off between polls: for producer-side warps of kernels whose epilogue is bound by
+// issue slots (a spinning warp takes ~1 slot in 5 from the four epilogue warps of its SM sub-partition).
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity, uint32_t ns) {
+  while (!mbar_try_wait(bar, parity)) asm volatile("nanosleep.u32 %0;" ::"r"(ns));
+}
+
 // ------------------------------------------------------------------ TMA ----
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

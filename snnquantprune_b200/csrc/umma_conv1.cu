@@ -15,7 +15,8 @@
 //
 // Pipeline: TMA (4 input rows x 144 B, zero-filled halo) -> 2 "patch" warps
 // gather the 32-byte K-rows into the canonical no-swizzle K-major layout ->
-// MMA warp -> 8 epilogue warps (membranes in registers across all T steps).
+// MMA warp -> 8 / 16 epilogue warps (membranes in registers across all T steps).
+#include <cstdio>
 #include <mutex>
 
 #include "common.cuh"
@@ -26,19 +27,34 @@ namespace snnqp {
 
 namespace {
 
+#ifdef SNNQP_C1_BISECT
+#define C1_T0() const long long _t0 = clock64()
+#define C1_ACC(var) var += clock64() - _t0
+#define C1_TIC(name) const long long name = clock64()
+#else
+#define C1_T0()
+#define C1_ACC(var)
+#define C1_TIC(name)
+#endif
+
 constexpr int kC = 128;
 constexpr int kQuadsPerTile = 32;
-constexpr int kEpiWarps = 8;
 constexpr int kPatchWarps = 2;
-constexpr int kThreads = (kEpiWarps + 2 + kPatchWarps) * 32;   // 384
+// EW epilogue warps (8: generic variant, 64 neurons per thread; 16: production variant, 32 neurons per thread --
+// four warps per SM sub-partition hide the fixed-latency / barrier / tcgen05.ld stalls that two could not)
+__host__ __device__ constexpr int threads_for(int ew) { return (ew + 2 + kPatchWarps) * 32; }
 // staging stage: 4 input rows x 160 B.  The TMA box must start on a 16-byte boundary in global memory
 // (an inner coordinate of -2 bytes faults with "illegal instruction"), so the box starts 16 bytes left of
 // the tile and the patch warps realign by 14 bytes with byte permutes.
 constexpr int kStRows = 4, kStRowBytes = 160, kStBytes = 640;
-constexpr int kStStages = 4;
-constexpr int kBStages = 2, kBBytes = 4096;                    // 32 quads x 128-byte swizzled rows (32 B used)
+constexpr int kStStages = 8;
+constexpr int kBStages = 4, kBBytes = 4096;                    // 32 quads x 128-byte swizzled rows (32 B used)
 constexpr int kWjBytes = kC * 128;                             // 128 rows x 128-byte swizzled rows (32 B used)
-constexpr int kTmemCols = 256;
+// Ring depths: the TMA -> patch -> MMA -> epilogue hand-offs are mbarrier round trips of ~1300 cycles per stage
+// (measured with every role reduced to its barriers: 2-deep rings cap the kernel at ~630 cycles per step whatever
+// the work), so both the operand ring and the accumulator ring are 4 deep: all 512 TMEM columns.
+constexpr int kAccStages = 4;
+constexpr int kTmemCols = 512;
 constexpr int kAccStride = 128;                                // 4 x 32 columns per buffer
 
 struct Conv1Args {
@@ -96,19 +112,21 @@ __device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {
 
 // FAST: standard LIF constants (tau 2, threshold 1, reset 0), pooled output, no
 // instrumentation outputs -- the production variant; !FAST handles everything else.
-template <bool FAST>
-__global__ void __launch_bounds__(kThreads, 1)
+template <bool FAST, int kEpiWarps>
+__global__ void __launch_bounds__(threads_for(kEpiWarps), 1)
 k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
+  constexpr int kThreads = threads_for(kEpiWarps);
+  constexpr int NQ = 128 / kEpiWarps;          // quads (accumulator columns per quad position) per epilogue thread
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t *w_smem = smem;                                   // 4 x 16 KB
   uint8_t *b_smem = smem + 4 * kWjBytes;                    // 2 x 4 KB
   uint8_t *st_smem = b_smem + kBStages * kBBytes;           // 4 x 640 B
   uint64_t *bars = reinterpret_cast<uint64_t *>(st_smem + kStStages * kStBytes);
-  uint32_t &tmem_slot = *reinterpret_cast<uint32_t *>(bars + 24);
+  uint32_t &tmem_slot = *reinterpret_cast<uint32_t *>(bars + 2 * (kStStages + kBStages + kAccStages));
   uint64_t *st_full = bars, *st_empty = bars + kStStages;
   uint64_t *b_full = bars + 2 * kStStages, *b_empty = b_full + kBStages;
-  uint64_t *acc_full = b_empty + kBStages, *acc_empty = acc_full + 2;
+  uint64_t *acc_full = b_empty + kBStages, *acc_empty = acc_full + kAccStages;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -127,7 +145,7 @@ k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
     ptx::prefetch_tmap(&tmap_x);
     for (int i = 0; i < kStStages; ++i) { ptx::mbar_init(st_full + i, 1); ptx::mbar_init(st_empty + i, kPatchWarps); }
     for (int i = 0; i < kBStages; ++i) { ptx::mbar_init(b_full + i, kPatchWarps); ptx::mbar_init(b_empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(acc_full + i, 1); ptx::mbar_init(acc_empty + i, kEpiWarps); }
+    for (int i = 0; i < kAccStages; ++i) { ptx::mbar_init(acc_full + i, 1); ptx::mbar_init(acc_empty + i, kEpiWarps); }
     ptx::fence_barrier_init();
   }
   if (warp == kEpiWarps + 1) ptx::tmem_alloc<kTmemCols>(&tmem_slot);
@@ -141,12 +159,15 @@ k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
     // ===================== TMA producer: 4 input rows x 144 B per step =====================
     if (ptx::elect_one()) {
       uint32_t step = 0;
+#ifdef SNNQP_C1_BISECT
+      long long w0 = 0; const long long tb = clock64();
+#endif
       for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
         const int tile = item % a.tiles_per_row, qh = (item / a.tiles_per_row) % QH;
         const int b = item / (a.tiles_per_row * QH);
         for (int t = 0; t < a.T; ++t, ++step) {
           const uint32_t s = step % kStStages, ph = (step / kStStages) & 1;
-          ptx::mbar_wait(st_empty + s, ph ^ 1);
+          { C1_T0(); ptx::mbar_wait_backoff(st_empty + s, ph ^ 1, 256); C1_ACC(w0); }
           if (a.debug & 2) { ptx::mbar_arrive(st_full + s); continue; }
           ptx::mbar_expect_tx(st_full + s, kStRows * kStRowBytes);
           // x coordinate in bytes of the (w, c) axis: patch of quad 0 starts at column 2*qw0 - 1
@@ -158,6 +179,9 @@ k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
               : "memory");
         }
       }
+#ifdef SNNQP_C1_BISECT
+      if (blockIdx.x == 0 && (a.debug & 64)) printf("TMA  : steps %u total %lld wait st_empty %lld\n", step, clock64() - tb, w0);
+#endif
     }
   } else if (warp == kEpiWarps + 1) {
     // ===================== MMA issuer: 4 x (128 x 32 x 32) per step =====================
@@ -165,13 +189,17 @@ k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
       const uint32_t idesc = make_idesc_f16(128, kQuadsPerTile);
       const uint32_t w_addr = ptx::smem_u32(w_smem), b_addr = ptx::smem_u32(b_smem);
       uint32_t step = 0;
+#ifdef SNNQP_C1_BISECT
+      long long w0 = 0, w1 = 0; const long long tb = clock64();
+#endif
       for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
         for (int t = 0; t < a.T; ++t, ++step) {
-          const uint32_t s = step & 1, ph = (step >> 1) & 1;
-          ptx::mbar_wait(acc_empty + s, ph ^ 1);
-          ptx::mbar_wait(b_full + s, ph);
+          const uint32_t s = step % kAccStages, ph = (step / kAccStages) & 1;
+          const uint32_t bs = step % kBStages, bph = (step / kBStages) & 1;
+          { C1_T0(); ptx::mbar_wait_backoff(acc_empty + s, ph ^ 1, 64); C1_ACC(w0); }
+          { C1_T0(); ptx::mbar_wait_backoff(b_full + bs, bph, 64); C1_ACC(w1); }
           ptx::tc_fence_after();
-          const uint64_t bd = ptx::make_desc_sw128(b_addr + s * kBBytes, 0);
+          const uint64_t bd = ptx::make_desc_sw128(b_addr + bs * kBBytes, 0);
           if (!(a.debug & 1)) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -181,22 +209,35 @@ k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
               mma_f16(tmem_base + s * kAccStride + j * kQuadsPerTile, ad + 2, bd + 2, idesc, 1);
             }
           }
-          ptx::mma_commit(b_empty + s);
+          ptx::mma_commit(b_empty + bs);
           ptx::mma_commit(acc_full + s);
         }
       }
+#ifdef SNNQP_C1_BISECT
+      if (blockIdx.x == 0 && (a.debug & 64)) printf("MMA  : steps %u total %lld wait acc_empty %lld wait b_full %lld\n", step, clock64() - tb, w0, w1);
+#endif
     }
   } else if (warp >= kEpiWarps + 2) {
     // ===================== patch warps: gather 32-byte K-rows =====================
     const int pt = threadIdx.x - (kEpiWarps + 2) * 32;     // 0..63
     const int quad = pt >> 1, half = pt & 1;               // K bytes 16*half .. +15 = patch rows 2*half, 2*half+1
     uint32_t step = 0;
+#ifdef SNNQP_C1_BISECT
+    long long w0 = 0, w1 = 0; const long long tb = clock64();
+#endif
     for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
       for (int t = 0; t < a.T; ++t, ++step) {
         const uint32_t s = step % kStStages, ph = (step / kStStages) & 1;
-        const uint32_t bs = step & 1, bph = (step >> 1) & 1;
-        ptx::mbar_wait(st_full + s, ph);
-        ptx::mbar_wait(b_empty + bs, bph ^ 1);
+        const uint32_t bs = step % kBStages, bph = (step / kBStages) & 1;
+        { C1_T0(); ptx::mbar_wait_backoff(st_full + s, ph, 64); C1_ACC(w0); }
+        { C1_T0(); ptx::mbar_wait_backoff(b_empty + bs, bph ^ 1, 64); C1_ACC(w1); }
+#ifdef SNNQP_C1_BISECT
+        if (a.debug & 32) {                         // bisection: no gather work
+          __syncwarp();
+          if (lane == 0) { ptx::mbar_arrive(b_full + bs); ptx::mbar_arrive(st_empty + s); }
+          continue;
+        }
+#endif
         // patch row bytes sit at offset 14 + 4*quad of the 160-byte staging row: three aligned words, realigned
         const uint32_t *src = reinterpret_cast<const uint32_t *>(st_smem + s * kStBytes + (2 * half) * kStRowBytes + 12 + 4 * quad);
         const uint32_t *src2 = reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(src) + kStRowBytes);
@@ -218,6 +259,9 @@ k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
         }
       }
     }
+#ifdef SNNQP_C1_BISECT
+    if (blockIdx.x == 0 && pt == 0 && (a.debug & 64)) printf("PATCH: steps %u total %lld wait st_full %lld wait b_empty %lld\n", step, clock64() - tb, w0, w1);
+#endif
   } else {
     // ===================== epilogue =====================
     const int q = warp & 3, g = warp >> 2;
@@ -225,88 +269,126 @@ k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
     const float sc = a.scale[c], bi = a.bias[c];
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const int Wo = a.pool ? a.W / 2 : a.W;
-    float u[4][16];                  // generic variant
-    uint64_t u2[4][8];               // FAST variant: packed pairs (quads 2p, 2p+1) per quad position j
-    const Lif2Consts k2(sc, bi, 1);
-    uint32_t step = 0;
-    for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
-      const int tile = item % a.tiles_per_row, qh = (item / a.tiles_per_row) % QH;
-      const int b = item / (a.tiles_per_row * QH);
-      const int qw0 = tile * kQuadsPerTile + 16 * g;        // first quad column of this thread
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int i = 0; i < 16; ++i) { u[j][i] = 0.0f; u2[j][i >> 1] = 0ull; }
-      for (int t = 0; t < a.T; ++t, ++step) {
-        const uint32_t s = step & 1, ph = (step >> 1) & 1;
-        ptx::mbar_wait(acc_full + s, ph);
-        ptx::tc_fence_after();
-        uint32_t acc[4][16];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t taddr = lane_addr + s * kAccStride + j * kQuadsPerTile + 16 * g;
-          SNNQP_TMEM_LD_X16(taddr, acc[j]);
-        }
-        ptx::tc_wait_ld();
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(acc_empty + s);
-
-        uint8_t *yb = a.spikes + (int64_t)t * a.y_stride_t + (int64_t)b * a.y_stride_b + c;
-        if constexpr (FAST) {
-          // Packed f32x2 LIF (FFMA2 / FADD2): ncu shows this kernel issue-bound (74.6 % issue slots, 6.5
-          // instructions per neuron); pairing neurons (i, i+1) of the same quad position j -- adjacent registers
-          // of one tcgen05.ld, so the pack is free -- brings it to ~4.1.  The fp32 accumulator needs no conversion.
-          uint8_t *yrow = yb + ((int64_t)qh * Wo + qw0) * kC;
-#pragma unroll
-          for (int p = 0; p < 8; ++p) {
-            uint64_t ssum = lif2_std_f32(u2[0][p], acc[0][2 * p], acc[0][2 * p + 1], k2);
-#pragma unroll
-            for (int j = 1; j < 4; ++j) ssum = add2(ssum, lif2_std_f32(u2[j][p], acc[j][2 * p], acc[j][2 * p + 1], k2));
-            float sa, sb;
-            unpack2(ssum, sa, sb);                       // number of spikes in quad 2p / 2p+1
-            yrow[(2 * p) * kC] = sa != 0.0f ? 1 : 0;
-            yrow[(2 * p + 1) * kC] = sb != 0.0f ? 1 : 0;
-          }
-          continue;
-        }
-        const LifParams<false> lif{a.tau, a.v_th, a.v_reset};
-        uint32_t m[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          m[j] = 0;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const bool sp = lif.step(u[j][i], __fmaf_rn(__uint_as_float(acc[j][i]), sc, bi));
-            m[j] |= (sp ? 1u : 0u) << i;
-          }
-        }
-        if (a.pool) {
-          const uint32_t mm = m[0] | m[1] | m[2] | m[3];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) yb[((int64_t)qh * Wo + qw0 + i) * kC] = (mm >> i) & 1u;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              yb[((int64_t)(2 * qh + (j >> 1)) * Wo + 2 * (qw0 + i) + (j & 1)) * kC] = (m[j] >> i) & 1u;
-        }
-        if (a.acc_dump) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              a.acc_dump[((((int64_t)t * a.B + b) * a.H + 2 * qh + (j >> 1)) * a.W + 2 * (qw0 + i) + (j & 1)) * kC + c] =
-                  __float2int_rn(__uint_as_float(acc[j][i]));
-        }
-      }
-      if (a.u_final) {
+    if constexpr (FAST) {
+      // Standard LIF, pooled output, fp32 accumulators (exact integers).  Everything on the FMA pipe is packed
+      // (FFMA2 / FADD2: two neurons = adjacent quads of one tcgen05.ld per instruction, 2 cycles each -- the same
+      // lane rate as scalar FFMA at half the issue slots; tools/ubench/fma_pipes.cu).  Per neuron: 4 FMA-pipe
+      // lane-ops (v, v - u, un, reset) + one FSET.BF on the half-rate ALU pipe; the 2x2 pool is an OR of the four
+      // spike words (two LOP3 per quad) and one shift.  The kernel is bound by issue slots, not by a pipe.
+      constexpr int NP = NQ / 2;
+      uint64_t u2[4][NP];
+      const uint64_t sc2 = pack2(sc, sc), bi2 = pack2(bi, bi), half2 = pack2(0.5f, 0.5f);
+      const uint32_t col0 = lane_addr + NQ * g;
+      // one LIF step of the neuron pair (quads 2p, 2p+1) at quad position j; returns the two spike words
+      auto lif_pair = [&](uint64_t &u, uint32_t a0, uint32_t a1, uint32_t &w0, uint32_t &w1) {
+        const uint64_t v = fma2(pack2(__uint_as_float(a0), __uint_as_float(a1)), sc2, bi2);
+        const uint64_t un = fma2(sub2(v, u), half2, u);
+        float ua, ub;
+        unpack2(un, ua, ub);
+        const float s0 = fset_ge1(ua), s1 = fset_ge1(ub);
+        u = fma2(pack2(-s0, -s1), un, un);
+        w0 = __float_as_uint(s0);
+        w1 = __float_as_uint(s1);
+      };
+      uint32_t step = 0;
+      for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
+        const int tile = item % a.tiles_per_row, qh = (item / a.tiles_per_row) % QH;
+        const int b = item / (a.tiles_per_row * QH);
+        const int qw0 = tile * kQuadsPerTile + NQ * g;        // first quad column of this thread
 #pragma unroll
         for (int j = 0; j < 4; ++j)
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            a.u_final[(((int64_t)b * a.H + 2 * qh + (j >> 1)) * a.W + 2 * (qw0 + i) + (j & 1)) * kC + c] = u[j][i];
+          for (int p = 0; p < NP; ++p) u2[j][p] = 0ull;
+        uint8_t *yrow = a.spikes + (int64_t)b * a.y_stride_b + c + ((int64_t)qh * Wo + qw0) * kC;
+        for (int t = 0; t < a.T; ++t, ++step, yrow += a.y_stride_t) {
+          const uint32_t s = step % kAccStages, ph = (step / kAccStages) & 1;
+          ptx::mbar_wait(acc_full + s, ph);
+          ptx::tc_fence_after();
+          uint32_t acc[4][NQ];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t taddr = col0 + s * kAccStride + j * kQuadsPerTile;
+            if constexpr (NQ == 16) { SNNQP_TMEM_LD_X16(taddr, acc[j]); } else { SNNQP_TMEM_LD_X8(taddr, acc[j]); }
+          }
+          ptx::tc_wait_ld();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(acc_empty + s);
+#pragma unroll
+          for (int p = 0; p < NP; ++p) {
+            uint32_t w[4][2];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) lif_pair(u2[j][p], acc[j][2 * p], acc[j][2 * p + 1], w[j][0], w[j][1]);
+            yrow[(2 * p) * kC] = (uint8_t)(((w[0][0] | w[1][0]) | (w[2][0] | w[3][0])) >> 29);   // 0x3F800000 >> 29 == 1
+            yrow[(2 * p + 1) * kC] = (uint8_t)(((w[0][1] | w[1][1]) | (w[2][1] | w[3][1])) >> 29);
+          }
+        }
+      }
+    } else {
+      float u[4][16];
+      uint32_t step = 0;
+      for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
+        const int tile = item % a.tiles_per_row, qh = (item / a.tiles_per_row) % QH;
+        const int b = item / (a.tiles_per_row * QH);
+        const int qw0 = tile * kQuadsPerTile + 16 * g;        // first quad column of this thread
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) u[j][i] = 0.0f;
+        for (int t = 0; t < a.T; ++t, ++step) {
+          const uint32_t s = step % kAccStages, ph = (step / kAccStages) & 1;
+          ptx::mbar_wait(acc_full + s, ph);
+          ptx::tc_fence_after();
+          uint32_t acc[4][16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t taddr = lane_addr + s * kAccStride + j * kQuadsPerTile + 16 * g;
+            SNNQP_TMEM_LD_X16(taddr, acc[j]);
+          }
+          ptx::tc_wait_ld();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(acc_empty + s);
+
+          uint8_t *yb = a.spikes + (int64_t)t * a.y_stride_t + (int64_t)b * a.y_stride_b + c;
+          const LifParams<false> lif{a.tau, a.v_th, a.v_reset};
+          uint32_t m[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            m[j] = 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const bool sp = lif.step(u[j][i], __fmaf_rn(__uint_as_float(acc[j][i]), sc, bi));
+              m[j] |= (sp ? 1u : 0u) << i;
+            }
+          }
+          if (a.pool) {
+            const uint32_t mm = m[0] | m[1] | m[2] | m[3];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) yb[((int64_t)qh * Wo + qw0 + i) * kC] = (mm >> i) & 1u;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                yb[((int64_t)(2 * qh + (j >> 1)) * Wo + 2 * (qw0 + i) + (j & 1)) * kC] = (m[j] >> i) & 1u;
+          }
+          if (a.acc_dump) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                a.acc_dump[((((int64_t)t * a.B + b) * a.H + 2 * qh + (j >> 1)) * a.W + 2 * (qw0 + i) + (j & 1)) * kC + c] =
+                    __float2int_rn(__uint_as_float(acc[j][i]));
+          }
+        }
+        if (a.u_final) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              a.u_final[(((int64_t)b * a.H + 2 * qh + (j >> 1)) * a.W + 2 * (qw0 + i) + (j & 1)) * kC + c] = u[j][i];
+        }
       }
     }
   }
@@ -383,14 +465,18 @@ int launch_conv1_umma(const snnqp_block_params &p, const uint8_t *x, const int8_
   a.wq4 = wq4; a.scale = scale; a.bias = bias;
   a.spikes = spikes; a.u_final = u_final; a.acc_dump = acc_dump;
   const int grid = a.total_items < sm_count() ? a.total_items : sm_count();
-  constexpr int kSmem = 4 * kWjBytes + kBStages * kBBytes + kStStages * kStBytes + 256 + 1024;
+  constexpr int kSmem = 4 * kWjBytes + kBStages * kBBytes + kStStages * kStBytes + 512 + 1024;
   const bool fast = p.tau == 2.0f && p.v_threshold == 1.0f && p.v_reset == 0.0f && p.pool && !u_final && !acc_dump;
-  if (fast) {
-    SNNQP_CUDA(cudaFuncSetAttribute(k_conv1_umma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    k_conv1_umma<true><<<grid, kThreads, kSmem, st>>>(tmx, a);
+  static const int ew_env = getenv("SNNQP_C1_EW") ? atoi(getenv("SNNQP_C1_EW")) : 16;
+  if (fast && ew_env == 16) {
+    SNNQP_CUDA(cudaFuncSetAttribute(k_conv1_umma<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    k_conv1_umma<true, 16><<<grid, threads_for(16), kSmem, st>>>(tmx, a);
+  } else if (fast) {
+    SNNQP_CUDA(cudaFuncSetAttribute(k_conv1_umma<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    k_conv1_umma<true, 8><<<grid, threads_for(8), kSmem, st>>>(tmx, a);
   } else {
-    SNNQP_CUDA(cudaFuncSetAttribute(k_conv1_umma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    k_conv1_umma<false><<<grid, kThreads, kSmem, st>>>(tmx, a);
+    SNNQP_CUDA(cudaFuncSetAttribute(k_conv1_umma<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    k_conv1_umma<false, 8><<<grid, threads_for(8), kSmem, st>>>(tmx, a);
   }
   SNNQP_POST_LAUNCH("k_conv1_umma");
   return SNNQP_OK;
