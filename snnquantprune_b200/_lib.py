@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsnnqp.so")
+# SNNQP_LIB: developer switch for same-box A/B timing of two builds (tools/); the product path is the in-tree .so
+LIB_PATH = os.environ.get("SNNQP_LIB") or os.path.join(_HERE, "libsnnqp.so")
 
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
 
