@@ -206,6 +206,13 @@ int snnqp_eval_metrics(const float *logits, const int32_t *labels, int B,
  * call with reset != 0 (bench.py's gpu_launches). */
 int64_t snnqp_launch_count(int reset);
 
+/* Diagnostic (no reference counterpart): dense int8 tensor-pipe ceiling of the
+ * current device -- back-to-back tcgen05.mma.kind::i8 128x256x32 from shared
+ * memory on every SM, best of `reps` launches of `iters` x 4 MMAs per SM, in
+ * TOP/s.  bench.py uses it as the roofline denominator of the tensor-bound
+ * kernels (MEASURED_PEAKS.json holds no int8 figure).  Synchronises `stream`. */
+int snnqp_diag_imma_peak(int iters, int reps, double *tops_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
