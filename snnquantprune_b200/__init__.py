@@ -11,7 +11,8 @@ from .spiking_learning import SpikingBlock, multi_step_LIF, atan, BatchNorm  # n
 from .models import CextNet, ModelConfig, eval_step  # noqa: F401
 from .pack import pack_cextnet  # noqa: F401
 from .engine import CextNetEngine  # noqa: F401
+from .eval import evaluate  # noqa: F401
 
 __all__ = ["DuQ", "prune", "gaussian_init", "max_init", "QuantConfig", "QuantConv", "QuantDense",
            "SpikingBlock", "multi_step_LIF", "atan", "BatchNorm", "CextNet", "ModelConfig",
-           "eval_step", "pack_cextnet", "CextNetEngine"]
+           "eval_step", "pack_cextnet", "CextNetEngine", "evaluate"]

@@ -654,3 +654,42 @@ def test_spiking_block_facade(cuda_lib, oracle_lib):
   u1, s1 = lif(u0, xin)
   ur, sr = ref_snn.lif_step(np.zeros(5, F32), xin.cpu().numpy())
   assert np.array_equal(u1.cpu().numpy(), ur) and np.array_equal(s1.cpu().numpy(), sr)
+
+
+def test_evaluate_driver_matches_oracle_metrics(cuda_lib):
+  """evaluate() (the reference's eval loop, examples/eval.py:53-139) over pinned host batches through
+  forward_host + snnqp_eval_metrics == compute_metrics of the oracle on the same logits."""
+  from snnquantprune_b200.eval import evaluate
+  bits, T, H, B = 8, 4, 32, 5
+  v = synthetic.make_variables(bits=bits, prune_percentage=0.5, T=T, H=H, seed=51)
+  eng = engine_for(v, bits, T, H, chunk=2)
+  rng = np.random.default_rng(52)
+  batches, losses, accs = [], [], []
+  for i in range(3):
+    fr = synthetic.make_frames(B, T, H, H, seed=60 + i)
+    lab = rng.integers(0, 11, size=B)
+    batches.append({"dvs_matrix": torch.as_tensor(fr).pin_memory(), "label": torch.as_tensor(lab)})
+    lg = eng.forward(dev(fr)).cpu().numpy()
+    m = ref_snn.eval_metrics(lg, lab)
+    losses.append(float(m["loss"])); accs.append(float(np.mean(m["accuracy"])))
+  got = evaluate(lambda f: eng.forward_host(f), batches, num_classes=11)
+  assert got["samples"] == 3 * B and got["steps"] == 3
+  assert np.isclose(got["loss"], np.mean(losses), rtol=1e-5)
+  assert np.isclose(got["accuracy"], np.mean(accs), atol=1e-7)
+
+
+def test_packed_file_round_trip_gives_identical_logits(cuda_lib, tmp_path):
+  """pack -> save_packed -> load_packed -> forward: the on-disk format is device-layout-exact."""
+  from snnquantprune_b200 import CextNetEngine, pack_cextnet
+  from snnquantprune_b200 import checkpoint_io as cio
+  bits, T, H, B = 4, 5, 64, 3
+  v = synthetic.make_variables(bits=bits, prune_percentage=0.8, T=T, H=H, seed=71)
+  fr = dev(synthetic.make_frames(B, T, H, H, seed=72))
+  pk = pack_cextnet(v, bits, T, H, device=DEV)
+  want = CextNetEngine(pk).forward(fr).cpu().numpy()
+  path = str(tmp_path / "net.snnqp")
+  cio.save_packed(pk, path)
+  back = cio.load_packed(path, device=DEV)
+  for k, t in cio._tensors_of(pk).items():
+    assert torch.equal(t, cio._tensors_of(back)[k]), k
+  assert np.array_equal(CextNetEngine(back).forward(fr).cpu().numpy(), want)

@@ -121,3 +121,71 @@ def test_world_size_2_gloo_sharding_and_reduction():
   [p.join(120) for p in procs]
   assert all(p.exitcode == 0 for p in procs)
   assert out.get(0) is True and out.get(1) is True
+
+
+# ---- evaluate(): the reference's eval loop (examples/eval.py:53-139) ----------------------------
+def _toy_forward(frames):
+  x = frames.float().mean(dim=(1, 2, 3))                        # (b, 2)
+  w = torch.arange(22, dtype=torch.float32).reshape(2, 11) / 7.0
+  return torch.sin(x @ w)
+
+
+def _torch_metrics(logits, labels, acc):
+  onehot = torch.nn.functional.one_hot(labels.long(), logits.shape[1]).float()
+  acc[0] += (logits.argmax(-1) == labels).float().sum()
+  acc[1] += ((logits - onehot) ** 2).sum()
+
+
+def _toy_batches(n_batches=3, B=6):
+  g = torch.Generator().manual_seed(5)
+  return [{"dvs_matrix": torch.randint(0, 5, (B, 4, 8, 8, 2), generator=g, dtype=torch.uint8),
+           "label": torch.randint(0, 11, (B,), generator=g)} for _ in range(n_batches)]
+
+
+def _eval_worker(rank, ws, port, out):
+  os.environ.update(RANK=str(rank), WORLD_SIZE=str(ws), LOCAL_RANK=str(rank),
+                    MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+  from snnquantprune_b200 import dist as D
+  from snnquantprune_b200.eval import evaluate
+  D.init(backend="gloo")
+  out[rank] = evaluate(_toy_forward, _toy_batches(), steps_per_eval=-1, metrics_fn=_torch_metrics)
+  torch.distributed.destroy_process_group()
+
+
+def test_evaluate_matches_reference_summary_single_and_sharded():
+  from snnquantprune_b200.eval import evaluate
+  batches = _toy_batches()
+  # the reference: per-step compute_metrics (mse_loss mean, accuracy vector), then the mean over everything
+  losses, accs = [], []
+  for b in batches:
+    lg = _toy_forward(b["dvs_matrix"])
+    oh = torch.nn.functional.one_hot(b["label"], 11).float()
+    losses.append(((lg - oh) ** 2).mean().item())
+    accs.append((lg.argmax(-1) == b["label"]).float().mean().item())
+  want = {"loss": float(np.mean(losses)), "accuracy": float(np.mean(accs))}
+  got = evaluate(_toy_forward, batches, metrics_fn=_torch_metrics)
+  assert got["samples"] == 18 and got["steps"] == 3
+  assert abs(got["loss"] - want["loss"]) < 1e-6 and abs(got["accuracy"] - want["accuracy"]) < 1e-6
+  assert evaluate(_toy_forward, batches, steps_per_eval=2, metrics_fn=_torch_metrics)["samples"] == 12
+  # world_size 2 (gloo): same summary on both ranks, one all-reduce
+  import torch.multiprocessing as mp
+  ctx = mp.get_context("spawn")
+  out = ctx.Manager().dict()
+  port = 29950 + os.getpid() % 40
+  procs = [ctx.Process(target=_eval_worker, args=(r, 2, port, out)) for r in range(2)]
+  [p.start() for p in procs]
+  [p.join(120) for p in procs]
+  assert all(p.exitcode == 0 for p in procs)
+  for r in range(2):
+    assert out[r]["samples"] == 18
+    assert abs(out[r]["loss"] - want["loss"]) < 1e-6 and abs(out[r]["accuracy"] - want["accuracy"]) < 1e-6
+
+
+def test_evaluate_rejects_indivisible_batch_like_reference():
+  from snnquantprune_b200.eval import evaluate
+  os.environ["WORLD_SIZE"] = "4"
+  try:
+    with pytest.raises(ValueError, match="divisible by the number of devices"):
+      evaluate(_toy_forward, _toy_batches(1, 6), metrics_fn=_torch_metrics)
+  finally:
+    del os.environ["WORLD_SIZE"]
