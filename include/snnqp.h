@@ -206,6 +206,30 @@ int snnqp_eval_metrics(const float *logits, const int32_t *labels, int B,
  * call with reset != 0 (bench.py's gpu_launches). */
 int64_t snnqp_launch_count(int reset);
 
+/* ---- rows next to the hot path ----------------------
+ * Event -> frame integration, "split by number" (examples/input_pipeline.py:
+ * 142-219 preprocess_data_number): addrs = int32 [N_total][3] (x, y, p) records
+ * of all samples back to back in time order, offsets = int64 [B+1] record
+ * offsets.  Sample b's events are cut into T groups of N_b / T events (the
+ * last takes the remainder); group t is histogrammed into frame (b, t):
+ * cell ((y/rs)*wh + x/rs, p != 0), wh = sensor_wh / rs.  frames: [B][T][wh][wh][2]
+ * uint8 saturating at 255 (out_int32 == 0; *n_saturated += saturated cells, may
+ * be NULL) or exact int32 (out_int32 != 0).  Like the reference, the FLAT
+ * position is histogrammed (an x beyond the row lands in the next row); only
+ * positions outside the frame are dropped (the reference's scatter would fail
+ * on them). */
+int snnqp_events_to_frames(const int32_t *addrs, const int64_t *offsets, int B,
+                           int T, int sensor_wh, int resolution_scale,
+                           void *frames, int out_int32, uint64_t *n_saturated,
+                           void *stream);
+
+/* Activation-density numerators (examples/tcja/models.py:128-142 sows
+ * sum(x != 0) over (H,W,C) per (t,b) slice / slice size, then max and mean):
+ * counts[i] = number of non-zero bytes of slice i (slice_bytes long, slices
+ * stride_slice apart).  counts is zeroed by the call. */
+int snnqp_slice_nonzeros(const uint8_t *x, int n_slices, int64_t slice_bytes,
+                         int64_t stride_slice, int32_t *counts, void *stream);
+
 /* Diagnostic (no reference counterpart): dense int8 tensor-pipe ceiling of the
  * current device -- back-to-back tcgen05.mma.kind::i8 128x256x32 from shared
  * memory on every SM, best of `reps` launches of `iters` x 4 MMAs per SM, in

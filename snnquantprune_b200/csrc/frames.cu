@@ -1,0 +1,129 @@
+// The rows either side of the hot path -- HBM-bound integer kernels.
+//
+// k_events_to_frames: DVS events -> event-count frames, "split by number"
+//   (reference examples/input_pipeline.py:142-219, preprocess_data_number): the N events of a sample are
+//   cut into T consecutive groups of di = N / T events (the last group takes the remainder), and each
+//   group is histogrammed into a (wh, wh, 2) frame: cell = ((y / rs) * wh + x / rs) * 2 + (p != 0).
+//   One CTA per (sample, frame): the whole 2*wh*wh int32 histogram lives in shared memory (128 KB at
+//   wh = 128), events are read once with coalesced 12-byte records, all atomics are shared-memory
+//   atomics, and the frame leaves as one pass of 128-bit stores in the hot path's own input layout
+//   [B][T][H][W][2] (uint8, saturating, saturated cells counted; or exact int32).
+//
+// k_slice_nonzeros: number of non-zero bytes of each (t, b) slice of a u8 activation tensor -- the
+//   numerator of the densities the reference sows (examples/tcja/models.py:128-142: sum(x != 0) over
+//   (H, W, C) per (t, b), then max / mean on the host).
+#include "common.cuh"
+
+namespace snnqp {
+namespace {
+
+template <typename OutT>
+__global__ void __launch_bounds__(512, 1)
+k_events_to_frames(const int32_t *__restrict__ addrs, const int64_t *__restrict__ offsets, int T, int wh, int rs,
+                   OutT *__restrict__ frames, unsigned long long *__restrict__ n_saturated) {
+  extern __shared__ int hist[];
+  const int b = blockIdx.x / T, t = blockIdx.x % T;
+  const int cells = 2 * wh * wh;
+  for (int i = threadIdx.x; i < cells / 4; i += blockDim.x) reinterpret_cast<int4 *>(hist)[i] = make_int4(0, 0, 0, 0);
+  __syncthreads();
+  const int64_t e0 = offsets[b], n = offsets[b + 1] - e0;
+  const int64_t di = n / T;
+  const int64_t lo = e0 + (int64_t)t * di, hi = (t < T - 1) ? lo + di : e0 + n;
+  // 12-byte records: three coalesced word streams
+  for (int64_t e = lo + threadIdx.x; e < hi; e += blockDim.x) {
+    const int x = __ldg(addrs + 3 * e) / rs, y = __ldg(addrs + 3 * e + 1) / rs, p = __ldg(addrs + 3 * e + 2);
+    // the reference histograms the FLAT position y*wh + x (input_pipeline.py:196-199): an x beyond the row
+    // lands in the next row, exactly as there; only positions outside the frame are dropped
+    const int64_t pos = (int64_t)y * wh + x;
+    if (pos >= 0 && pos < (int64_t)wh * wh) atomicAdd(hist + (pos << 1) + (p != 0 ? 1 : 0), 1);
+  }
+  __syncthreads();
+  OutT *dst = frames + ((int64_t)b * T + t) * cells;
+  if constexpr (sizeof(OutT) == 4) {
+    for (int i = threadIdx.x; i < cells / 4; i += blockDim.x)
+      reinterpret_cast<int4 *>(dst)[i] = reinterpret_cast<const int4 *>(hist)[i];
+  } else {
+    unsigned sat = 0;
+    for (int i = threadIdx.x; i < cells / 16; i += blockDim.x) {
+      uint32_t w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int4 v = reinterpret_cast<const int4 *>(hist)[4 * i + k];
+        sat += (v.x > 255) + (v.y > 255) + (v.z > 255) + (v.w > 255);
+        w[k] = (uint32_t)min(v.x, 255) | ((uint32_t)min(v.y, 255) << 8) | ((uint32_t)min(v.z, 255) << 16) |
+               ((uint32_t)min(v.w, 255) << 24);
+      }
+      reinterpret_cast<uint4 *>(dst)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    if (n_saturated) {
+      for (int off = 16; off > 0; off >>= 1) sat += __shfl_xor_sync(0xffffffffu, sat, off);
+      if ((threadIdx.x & 31) == 0 && sat) atomicAdd(n_saturated, (unsigned long long)sat);
+    }
+  }
+}
+
+// grid: (blocks_per_slice, n_slices); 16 bytes per thread per iteration
+__global__ void __launch_bounds__(256)
+k_slice_nonzeros(const uint8_t *__restrict__ x, int64_t slice_bytes, int64_t stride_slice, int32_t *__restrict__ counts) {
+  const uint8_t *base = x + (int64_t)blockIdx.y * stride_slice;
+  const int64_t n16 = slice_bytes / 16;
+  int c = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(base) + i);
+    // non-zero bytes of a word: (b | (b + 0x7F..)) bit 7 per byte
+    auto nzb = [](uint32_t w) { return __popc(((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu | w) & 0x80808080u); };
+    c += nzb(v.x) + nzb(v.y) + nzb(v.z) + nzb(v.w);
+  }
+  if (blockIdx.x == 0)
+    for (int64_t i = n16 * 16 + threadIdx.x; i < slice_bytes; i += blockDim.x) c += base[i] != 0;
+  for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(counts + blockIdx.y, c);
+}
+
+}  // namespace
+}  // namespace snnqp
+
+extern "C" int snnqp_events_to_frames(const int32_t *addrs, const int64_t *offsets, int B, int T, int sensor_wh,
+                                      int resolution_scale, void *frames, int out_int32, uint64_t *n_saturated,
+                                      void *stream_) {
+  using namespace snnqp;
+  if (int r = require_device()) return r;
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  if (!addrs || !offsets || !frames) return invalid("snnqp_events_to_frames: null pointer");
+  if (B <= 0 || T <= 0 || sensor_wh <= 0 || resolution_scale <= 0) return invalid("snnqp_events_to_frames: B, T, wh, scale must be > 0");
+  const int wh = sensor_wh / resolution_scale;
+  if (wh <= 0 || (2 * wh * wh) % 16) return invalid("snnqp_events_to_frames: 2*wh*wh must be a multiple of 16 (wh = %d)", wh);
+  const size_t smem = (size_t)2 * wh * wh * sizeof(int);
+  if (smem > 200 * 1024) return unsupported("snnqp_events_to_frames: frame of %d x %d x 2 does not fit the shared-memory histogram", wh, wh);
+  if (reinterpret_cast<uintptr_t>(frames) & 15) return invalid("snnqp_events_to_frames: frames must be 16-byte aligned");
+  if (out_int32) {
+    SNNQP_CUDA(cudaFuncSetAttribute(k_events_to_frames<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_events_to_frames<int32_t><<<B * T, 512, smem, st>>>(addrs, offsets, T, wh, resolution_scale,
+                                                            static_cast<int32_t *>(frames), nullptr);
+  } else {
+    SNNQP_CUDA(cudaFuncSetAttribute(k_events_to_frames<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_events_to_frames<uint8_t><<<B * T, 512, smem, st>>>(addrs, offsets, T, wh, resolution_scale,
+                                                            static_cast<uint8_t *>(frames),
+                                                            reinterpret_cast<unsigned long long *>(n_saturated));
+  }
+  SNNQP_POST_LAUNCH("k_events_to_frames");
+  return SNNQP_OK;
+}
+
+extern "C" int snnqp_slice_nonzeros(const uint8_t *x, int n_slices, int64_t slice_bytes, int64_t stride_slice,
+                                    int32_t *counts, void *stream_) {
+  using namespace snnqp;
+  if (int r = require_device()) return r;
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  if (!x || !counts) return invalid("snnqp_slice_nonzeros: null pointer");
+  if (n_slices <= 0 || slice_bytes <= 0) return invalid("snnqp_slice_nonzeros: n_slices and slice_bytes must be > 0");
+  if (n_slices > 65535) return unsupported("snnqp_slice_nonzeros: more than 65535 slices");
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (stride_slice & 15)) return invalid("snnqp_slice_nonzeros: x and the slice stride must be 16-byte aligned");
+  SNNQP_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * n_slices, st));
+  int bx = (int)((slice_bytes / 16 + 255) / 256);
+  const int cap = (8 * sm_count() + n_slices - 1) / n_slices;          // ~8 CTAs per SM over the whole grid
+  bx = bx < 1 ? 1 : (bx > cap ? (cap < 1 ? 1 : cap) : bx);
+  k_slice_nonzeros<<<dim3(bx, n_slices), 256, 0, st>>>(x, slice_bytes, stride_slice, counts);
+  SNNQP_POST_LAUNCH("k_slice_nonzeros");
+  return SNNQP_OK;
+}

@@ -1,0 +1,79 @@
+"""Event -> frame integration in front of the hot path, with the reference's
+entry-point name and argument meaning
+(/root/reference/examples/input_pipeline.py:142-219 ``preprocess_data_number``;
+``split_by == "number"`` only -- the reference raises NotImplementedError for
+"time" too), on the GPU: the frames are produced directly in HBM in the hot
+path's input layout (B,T,H,W,2) uint8, so real event streams never touch a CPU
+histogram.  No CPU fallback."""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def concat_events(samples: Sequence[np.ndarray]) -> Tuple[torch.Tensor, torch.Tensor]:
+  """Host side of a ragged batch: list of (N_b, 3) integer (x, y, p) arrays in time order ->
+  (pinned int32 [N_total, 3], pinned int64 [B+1] offsets)."""
+  sizes = [int(np.shape(a)[0]) for a in samples]
+  offsets = torch.zeros(len(samples) + 1, dtype=torch.int64)
+  offsets[1:] = torch.as_tensor(np.cumsum(sizes))
+  flat = np.concatenate([np.asarray(a).reshape(-1, 3) for a in samples], 0).astype(np.int32, copy=False) \
+      if sum(sizes) else np.zeros((0, 3), np.int32)
+  addrs = torch.as_tensor(np.ascontiguousarray(flat))
+  if torch.cuda.is_available():
+    addrs, offsets = addrs.pin_memory(), offsets.pin_memory()
+  return addrs, offsets
+
+
+def events_to_frames(addrs: torch.Tensor, offsets: torch.Tensor, num_frames: int, wh: int,
+                     resolution_scale: int = 1, exact_int32: bool = False,
+                     out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+  """Device tensors in, device frames out: (B, T, wh', wh', 2) uint8 (saturating at 255) or int32.
+  Returns (frames, n_saturated) with n_saturated a device int64 scalar (no host sync)."""
+  if int(resolution_scale) != resolution_scale or resolution_scale < 1:
+    raise NotImplementedError("resolution_scale must be a positive integer")
+  if addrs.dtype != torch.int32 or offsets.dtype != torch.int64:
+    raise ValueError("addrs must be int32 (N,3) and offsets int64 (B+1,)")
+  B = offsets.numel() - 1
+  whs = int(wh // resolution_scale)
+  dt = torch.int32 if exact_int32 else torch.uint8
+  if out is None:
+    out = torch.empty((B, num_frames, whs, whs, 2), device=addrs.device, dtype=dt)
+  sat = torch.zeros((), device=addrs.device, dtype=torch.int64)
+  if B == 0:
+    return out, sat
+  _lib.check(_lib.lib().snnqp_events_to_frames(_lib.ptr(addrs), _lib.ptr(offsets), B, num_frames, int(wh),
+                                               int(resolution_scale), _lib.ptr(out), 1 if exact_int32 else 0,
+                                               _lib.ptr(sat), _lib.stream()))
+  return out, sat
+
+
+def preprocess_data_number(addrs, times, config, wh, device="cuda") -> torch.Tensor:
+  """One sample, reference signature: addrs (N,3) (x,y,p), ``times`` unused by the
+  number split (as in the reference), config.num_frames / config.resolution_scale /
+  config.split_by.  Returns (T, wh', wh', 2) uint8 on ``device``."""
+  if getattr(config, "split_by", "number") != "number":
+    raise NotImplementedError
+  a, off = concat_events([np.asarray(addrs)])
+  fr, _ = events_to_frames(a.to(device, non_blocking=True), off.to(device, non_blocking=True),
+                           int(config.num_frames), int(wh), int(getattr(config, "resolution_scale", 1)))
+  return fr[0]
+
+
+def density_stats(x: torch.Tensor, n_slices: int) -> dict:
+  """The densities the reference sows per layer (examples/tcja/models.py:128-142): ``x`` is a
+  contiguous uint8 device tensor whose leading ``n_slices`` = T*B (or B*T) slices are the
+  (t, b) units.  Returns device tensors {"counts" int32 [n_slices], "min", "mean"} ('_min' is
+  the max density, as in the reference's naming)."""
+  if x.dtype != torch.uint8 or not x.is_contiguous():
+    raise ValueError("density_stats takes a contiguous uint8 tensor")
+  slice_bytes = x.numel() // n_slices
+  counts = torch.empty(n_slices, device=x.device, dtype=torch.int32)
+  _lib.check(_lib.lib().snnqp_slice_nonzeros(_lib.ptr(x), n_slices, slice_bytes, slice_bytes, _lib.ptr(counts),
+                                             _lib.stream()))
+  frac = counts.to(torch.float64) / float(slice_bytes)
+  return {"counts": counts, "min": frac.max(), "mean": frac.mean()}

@@ -1,0 +1,108 @@
+"""Event -> frame integration (reference examples/input_pipeline.py:142-219) and sowed densities
+(examples/tcja/models.py:128-142): oracle pinned by hand-computed cases and properties on the CPU,
+CUDA kernels bit-exact against the oracle on the GPU (through the C-ABI)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_events
+
+
+def _events(rng, n, wh, p_out=0.0):
+  a = np.stack([rng.integers(0, wh, n), rng.integers(0, wh, n), rng.integers(0, 2, n)], 1).astype(np.int32)
+  if p_out and n:
+    k = rng.random(n) < p_out
+    a[k, 0] = wh + rng.integers(0, 5, k.sum())          # outside the sensor
+  return a
+
+
+def test_oracle_hand_case_split_by_number():
+  # 7 events, T = 3 -> di = 2: frames take events [0,2), [2,4), [4,7)  (input_pipeline.py:166-178)
+  addrs = np.array([[0, 0, 1], [1, 0, 0], [1, 1, 1], [1, 1, 1], [0, 1, 0], [0, 1, 0], [3, 3, 5]], np.int32)
+  f = ref_events.preprocess_data_number(addrs, 3, 4)
+  assert f.shape == (3, 4, 4, 2) and f.dtype == np.int32
+  want = np.zeros((3, 4, 4, 2), np.int32)
+  want[0, 0, 0, 1] = 1; want[0, 0, 1, 0] = 1            # [t, y, x, polarity != 0]
+  want[1, 1, 1, 1] = 2
+  want[2, 1, 0, 0] = 2; want[2, 3, 3, 1] = 1            # p = 5 counts as "not 0"
+  assert np.array_equal(f, want)
+  # resolution_scale 2: (x, y) -> (x // 2, y // 2) on a 2 x 2 grid
+  f2 = ref_events.preprocess_data_number(addrs, 3, 4, 2)
+  assert f2.shape == (3, 2, 2, 2) and f2.sum() == 7 and f2[2, 1, 1, 1] == 1 and f2[1, 0, 0, 1] == 2
+
+
+def test_oracle_properties():
+  rng = np.random.default_rng(0)
+  for n, T, wh in [(1000, 20, 16), (19, 20, 8), (0, 5, 8), (4001, 10, 32)]:
+    a = _events(rng, n, wh)
+    f = ref_events.preprocess_data_number(a, T, wh)
+    assert f.sum() == n                                           # every in-range event lands once
+    di = n // T
+    per = f.reshape(T, -1).sum(1)
+    assert list(per[:-1]) == [di] * (T - 1) and per[-1] == n - di * (T - 1)
+    assert f[..., 1].sum() == (a[:, 2] != 0).sum()
+  d = ref_events.sow_densities(np.array([[[1, 0, 0, 2]], [[0, 0, 0, 0]]]))     # (T=2, B=1, 4)
+  assert d["min"] == 0.5 and d["mean"] == 0.25 and d["counts"].tolist() == [[2], [0]]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("wh,rs,T", [(128, 1, 20), (128, 4, 10), (64, 2, 7)])
+def test_events_to_frames_bit_exact(cuda_lib, wh, rs, T):
+  from snnquantprune_b200 import input_pipeline as ip
+  rng = np.random.default_rng(wh + rs)
+  sizes = [30000, 0, 13, T, 50001, 1]
+  samples = [_events(rng, n, wh, p_out=0.01) for n in sizes]
+  samples[4][:4000, :2] = [5, 9]                                   # one hot pixel -> uint8 saturation
+  addrs, off = ip.concat_events(samples)
+  want32 = ref_events.batch_to_frames(samples, T, wh, rs)
+  got32, _ = ip.events_to_frames(addrs.cuda(), off.cuda(), T, wh, rs, exact_int32=True)
+  assert np.array_equal(got32.cpu().numpy(), want32)
+  want8, nsat = ref_events.batch_to_frames(samples, T, wh, rs, saturate_u8=True)
+  got8, sat = ip.events_to_frames(addrs.cuda(), off.cuda(), T, wh, rs)
+  assert got8.dtype == torch.uint8 and np.array_equal(got8.cpu().numpy(), want8)
+  assert int(sat.item()) == nsat and nsat > 0
+
+
+@pytest.mark.gpu
+def test_preprocess_data_number_reference_signature_and_errors(cuda_lib):
+  from types import SimpleNamespace
+  from snnquantprune_b200 import input_pipeline as ip
+  rng = np.random.default_rng(5)
+  a = _events(rng, 5000, 128)
+  cfg = SimpleNamespace(num_frames=20, resolution_scale=1, split_by="number")
+  f = ip.preprocess_data_number(a, None, cfg, 128)
+  assert np.array_equal(f.cpu().numpy(), np.minimum(ref_events.preprocess_data_number(a, 20, 128), 255))
+  with pytest.raises(NotImplementedError):
+    ip.preprocess_data_number(a, None, SimpleNamespace(num_frames=20, split_by="time"), 128)
+  with pytest.raises(ValueError):
+    ip.events_to_frames(torch.zeros((4, 3), dtype=torch.int64).cuda(), torch.zeros(2, dtype=torch.int64).cuda(), 4, 32)
+  from snnquantprune_b200 import _lib
+  rc = _lib.lib().snnqp_events_to_frames(None, None, 1, 1, 32, 1, None, 0, None, None)
+  assert rc != 0 and b"null pointer" in _lib.lib().snnqp_last_error()
+
+
+@pytest.mark.gpu
+def test_events_feed_the_hot_path(cuda_lib):
+  """events -> frames (GPU) -> forward == forward on the oracle-integrated frames."""
+  from snnquantprune_b200 import CextNetEngine, pack_cextnet, synthetic, input_pipeline as ip
+  bits, T, H, B = 8, 4, 32, 3
+  rng = np.random.default_rng(9)
+  samples = [_events(rng, n, H) for n in (900, 1500, 400)]
+  addrs, off = ip.concat_events(samples)
+  fr, _ = ip.events_to_frames(addrs.cuda(), off.cuda(), T, H)
+  want = ref_events.batch_to_frames(samples, T, H, 1, saturate_u8=True)[0]
+  v = synthetic.make_variables(bits=bits, prune_percentage=0.5, T=T, H=H, seed=1)
+  eng = CextNetEngine(pack_cextnet(v, bits, T, H, device="cuda"))
+  assert np.array_equal(eng.forward(fr).cpu().numpy(), eng.forward(torch.as_tensor(want).cuda()).cpu().numpy())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(4, 3, 16, 16, 128), (2, 5, 7, 16), (20, 2, 64, 64, 128)])
+def test_density_stats_bit_exact(cuda_lib, shape):
+  from snnquantprune_b200 import input_pipeline as ip
+  rng = np.random.default_rng(len(shape))
+  x = (rng.random(shape) < 0.13).astype(np.uint8) * rng.integers(1, 256, shape).astype(np.uint8)
+  d = ip.density_stats(torch.as_tensor(x).cuda(), shape[0] * shape[1])
+  w = ref_events.sow_densities(x)
+  assert np.array_equal(d["counts"].cpu().numpy().reshape(shape[:2]), w["counts"])
+  assert abs(d["min"].item() - w["min"]) < 1e-12 and abs(d["mean"].item() - w["mean"]) < 1e-12
