@@ -217,11 +217,14 @@ int64_t snnqp_launch_count(int reset);
  * be NULL) or exact int32 (out_int32 != 0).  Like the reference, the FLAT
  * position is histogrammed (an x beyond the row lands in the next row); only
  * positions outside the frame are dropped (the reference's scatter would fail
- * on them). */
+ * on them).  max_events_per_sample: an upper bound of offsets[b+1]-offsets[b]
+ * known to the caller (it built the offsets), or 0 if unknown; when it proves
+ * every frame holds < 65536 events the histogram uses 16-bit counters (three
+ * frames in flight per SM instead of one).  Results are identical either way. */
 int snnqp_events_to_frames(const int32_t *addrs, const int64_t *offsets, int B,
                            int T, int sensor_wh, int resolution_scale,
-                           void *frames, int out_int32, uint64_t *n_saturated,
-                           void *stream);
+                           int64_t max_events_per_sample, void *frames,
+                           int out_int32, uint64_t *n_saturated, void *stream);
 
 /* Activation-density numerators (examples/tcja/models.py:128-142 sows
  * sum(x != 0) over (H,W,C) per (t,b) slice / slice size, then max and mean):

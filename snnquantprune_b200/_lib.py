@@ -58,7 +58,7 @@ SIGNATURES = {
     "snnqp_maxpool2_fwd": (_i, [_BP, _vp, _vp, _vp]),
     "snnqp_vote_fwd": (_i, [_vp, _i, _i, _i, _i, _i64, _i64, _vp, _vp]),
     "snnqp_eval_metrics": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
-    "snnqp_events_to_frames": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
+    "snnqp_events_to_frames": (_i, [_vp, _vp, _i, _i, _i, _i, _i64, _vp, _i, _vp, _vp]),
     "snnqp_slice_nonzeros": (_i, [_vp, _i, _i64, _i64, _vp, _vp]),
     "snnqp_diag_imma_peak": (_i, [_i, _i, C.POINTER(C.c_double), _vp]),
 }

@@ -4,8 +4,8 @@
 //   (reference examples/input_pipeline.py:142-219, preprocess_data_number): the N events of a sample are
 //   cut into T consecutive groups of di = N / T events (the last group takes the remainder), and each
 //   group is histogrammed into a (wh, wh, 2) frame: cell = ((y / rs) * wh + x / rs) * 2 + (p != 0).
-//   One CTA per (sample, frame): the whole 2*wh*wh int32 histogram lives in shared memory (128 KB at
-//   wh = 128), events are read once with coalesced 12-byte records, all atomics are shared-memory
+//   One CTA per (sample, frame): the whole histogram lives in shared memory (64 KB at wh = 128 with 16-bit
+//   counters -- three frames in flight per SM; 128 KB with 32-bit ones), events are read once with coalesced 12-byte records, all atomics are shared-memory
 //   atomics, and the frame leaves as one pass of 128-bit stores in the hot path's own input layout
 //   [B][T][H][W][2] (uint8, saturating, saturated cells counted; or exact int32).
 //
@@ -17,14 +17,18 @@
 namespace snnqp {
 namespace {
 
-template <typename OutT>
-__global__ void __launch_bounds__(512, 1)
+// PACKED: the two polarity counters of a pixel share one 32-bit word (16 bits each) -- 64 KB per frame at
+// wh = 128, three CTAs per SM; exact while a frame holds < 65536 events (the launcher checks the caller's bound).
+// !PACKED: one int32 per cell (128 KB, one CTA per SM), exact for any count.
+template <typename OutT, bool PACKED>
+__global__ void __launch_bounds__(512, PACKED ? 3 : 1)
 k_events_to_frames(const int32_t *__restrict__ addrs, const int64_t *__restrict__ offsets, int T, int wh, int rs,
                    OutT *__restrict__ frames, unsigned long long *__restrict__ n_saturated) {
   extern __shared__ int hist[];
   const int b = blockIdx.x / T, t = blockIdx.x % T;
-  const int cells = 2 * wh * wh;
-  for (int i = threadIdx.x; i < cells / 4; i += blockDim.x) reinterpret_cast<int4 *>(hist)[i] = make_int4(0, 0, 0, 0);
+  const int pixels = wh * wh;
+  const int words = PACKED ? pixels : 2 * pixels;
+  for (int i = threadIdx.x; i < words / 4; i += blockDim.x) reinterpret_cast<int4 *>(hist)[i] = make_int4(0, 0, 0, 0);
   __syncthreads();
   const int64_t e0 = offsets[b], n = offsets[b + 1] - e0;
   const int64_t di = n / T;
@@ -35,20 +39,32 @@ k_events_to_frames(const int32_t *__restrict__ addrs, const int64_t *__restrict_
     // the reference histograms the FLAT position y*wh + x (input_pipeline.py:196-199): an x beyond the row
     // lands in the next row, exactly as there; only positions outside the frame are dropped
     const int64_t pos = (int64_t)y * wh + x;
-    if (pos >= 0 && pos < (int64_t)wh * wh) atomicAdd(hist + (pos << 1) + (p != 0 ? 1 : 0), 1);
+    if (pos >= 0 && pos < (int64_t)pixels) {
+      if constexpr (PACKED) atomicAdd(hist + pos, p != 0 ? 0x10000 : 1);
+      else atomicAdd(hist + (pos << 1) + (p != 0 ? 1 : 0), 1);
+    }
   }
   __syncthreads();
+  // cell c of the frame = (pixel c >> 1, polarity c & 1)
+  auto cell4 = [&](int i) {          // cells 4i .. 4i+3
+    if constexpr (PACKED) {
+      const int2 w = reinterpret_cast<const int2 *>(hist)[i];
+      return make_int4(w.x & 0xFFFF, (int)((uint32_t)w.x >> 16), w.y & 0xFFFF, (int)((uint32_t)w.y >> 16));
+    } else {
+      return reinterpret_cast<const int4 *>(hist)[i];
+    }
+  };
+  const int cells = 2 * pixels;
   OutT *dst = frames + ((int64_t)b * T + t) * cells;
   if constexpr (sizeof(OutT) == 4) {
-    for (int i = threadIdx.x; i < cells / 4; i += blockDim.x)
-      reinterpret_cast<int4 *>(dst)[i] = reinterpret_cast<const int4 *>(hist)[i];
+    for (int i = threadIdx.x; i < cells / 4; i += blockDim.x) reinterpret_cast<int4 *>(dst)[i] = cell4(i);
   } else {
     unsigned sat = 0;
     for (int i = threadIdx.x; i < cells / 16; i += blockDim.x) {
       uint32_t w[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int4 v = reinterpret_cast<const int4 *>(hist)[4 * i + k];
+        const int4 v = cell4(4 * i + k);
         sat += (v.x > 255) + (v.y > 255) + (v.z > 255) + (v.w > 255);
         w[k] = (uint32_t)min(v.x, 255) | ((uint32_t)min(v.y, 255) << 8) | ((uint32_t)min(v.z, 255) << 16) |
                ((uint32_t)min(v.w, 255) << 24);
@@ -83,9 +99,21 @@ k_slice_nonzeros(const uint8_t *__restrict__ x, int64_t slice_bytes, int64_t str
 }  // namespace
 }  // namespace snnqp
 
+namespace snnqp {
+template <typename OutT, bool PACKED>
+static int launch_events(const int32_t *addrs, const int64_t *offsets, int B, int T, int wh, int rs, OutT *frames,
+                         unsigned long long *n_sat, cudaStream_t st) {
+  const size_t smem = (size_t)(PACKED ? 1 : 2) * wh * wh * sizeof(int);
+  SNNQP_CUDA(cudaFuncSetAttribute(k_events_to_frames<OutT, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_events_to_frames<OutT, PACKED><<<B * T, 512, smem, st>>>(addrs, offsets, T, wh, rs, frames, n_sat);
+  SNNQP_POST_LAUNCH("k_events_to_frames");
+  return SNNQP_OK;
+}
+}  // namespace snnqp
+
 extern "C" int snnqp_events_to_frames(const int32_t *addrs, const int64_t *offsets, int B, int T, int sensor_wh,
-                                      int resolution_scale, void *frames, int out_int32, uint64_t *n_saturated,
-                                      void *stream_) {
+                                      int resolution_scale, int64_t max_events_per_sample, void *frames, int out_int32,
+                                      uint64_t *n_saturated, void *stream_) {
   using namespace snnqp;
   if (int r = require_device()) return r;
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
@@ -93,21 +121,20 @@ extern "C" int snnqp_events_to_frames(const int32_t *addrs, const int64_t *offse
   if (B <= 0 || T <= 0 || sensor_wh <= 0 || resolution_scale <= 0) return invalid("snnqp_events_to_frames: B, T, wh, scale must be > 0");
   const int wh = sensor_wh / resolution_scale;
   if (wh <= 0 || (2 * wh * wh) % 16) return invalid("snnqp_events_to_frames: 2*wh*wh must be a multiple of 16 (wh = %d)", wh);
-  const size_t smem = (size_t)2 * wh * wh * sizeof(int);
-  if (smem > 200 * 1024) return unsupported("snnqp_events_to_frames: frame of %d x %d x 2 does not fit the shared-memory histogram", wh, wh);
+  if ((size_t)2 * wh * wh * sizeof(int) > 200 * 1024)
+    return unsupported("snnqp_events_to_frames: frame of %d x %d x 2 does not fit the shared-memory histogram", wh, wh);
   if (reinterpret_cast<uintptr_t>(frames) & 15) return invalid("snnqp_events_to_frames: frames must be 16-byte aligned");
+  // a frame holds at most N/T + (T-1) events: 16-bit counters are exact below 65536
+  const bool packed = max_events_per_sample > 0 && max_events_per_sample / T + T < 65536;
+  unsigned long long *ns = reinterpret_cast<unsigned long long *>(n_saturated);
   if (out_int32) {
-    SNNQP_CUDA(cudaFuncSetAttribute(k_events_to_frames<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_events_to_frames<int32_t><<<B * T, 512, smem, st>>>(addrs, offsets, T, wh, resolution_scale,
-                                                            static_cast<int32_t *>(frames), nullptr);
-  } else {
-    SNNQP_CUDA(cudaFuncSetAttribute(k_events_to_frames<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_events_to_frames<uint8_t><<<B * T, 512, smem, st>>>(addrs, offsets, T, wh, resolution_scale,
-                                                            static_cast<uint8_t *>(frames),
-                                                            reinterpret_cast<unsigned long long *>(n_saturated));
+    int32_t *f = static_cast<int32_t *>(frames);
+    return packed ? launch_events<int32_t, true>(addrs, offsets, B, T, wh, resolution_scale, f, nullptr, st)
+                  : launch_events<int32_t, false>(addrs, offsets, B, T, wh, resolution_scale, f, nullptr, st);
   }
-  SNNQP_POST_LAUNCH("k_events_to_frames");
-  return SNNQP_OK;
+  uint8_t *f = static_cast<uint8_t *>(frames);
+  return packed ? launch_events<uint8_t, true>(addrs, offsets, B, T, wh, resolution_scale, f, ns, st)
+                : launch_events<uint8_t, false>(addrs, offsets, B, T, wh, resolution_scale, f, ns, st);
 }
 
 extern "C" int snnqp_slice_nonzeros(const uint8_t *x, int n_slices, int64_t slice_bytes, int64_t stride_slice,

@@ -55,12 +55,13 @@ def test_events_to_frames_bit_exact(cuda_lib, wh, rs, T):
   samples[4][:4000, :2] = [5, 9]                                   # one hot pixel -> uint8 saturation
   addrs, off = ip.concat_events(samples)
   want32 = ref_events.batch_to_frames(samples, T, wh, rs)
-  got32, _ = ip.events_to_frames(addrs.cuda(), off.cuda(), T, wh, rs, exact_int32=True)
-  assert np.array_equal(got32.cpu().numpy(), want32)
   want8, nsat = ref_events.batch_to_frames(samples, T, wh, rs, saturate_u8=True)
-  got8, sat = ip.events_to_frames(addrs.cuda(), off.cuda(), T, wh, rs)
-  assert got8.dtype == torch.uint8 and np.array_equal(got8.cpu().numpy(), want8)
-  assert int(sat.item()) == nsat and nsat > 0
+  for bound in (0, max(sizes), 10**9):          # 32-bit counters / 16-bit packed counters / bound too large to pack
+    got32, _ = ip.events_to_frames(addrs.cuda(), off.cuda(), T, wh, rs, exact_int32=True, max_events_per_sample=bound)
+    assert np.array_equal(got32.cpu().numpy(), want32), bound
+    got8, sat = ip.events_to_frames(addrs.cuda(), off.cuda(), T, wh, rs, max_events_per_sample=bound)
+    assert got8.dtype == torch.uint8 and np.array_equal(got8.cpu().numpy(), want8), bound
+    assert int(sat.item()) == nsat and nsat > 0
 
 
 @pytest.mark.gpu
@@ -77,7 +78,7 @@ def test_preprocess_data_number_reference_signature_and_errors(cuda_lib):
   with pytest.raises(ValueError):
     ip.events_to_frames(torch.zeros((4, 3), dtype=torch.int64).cuda(), torch.zeros(2, dtype=torch.int64).cuda(), 4, 32)
   from snnquantprune_b200 import _lib
-  rc = _lib.lib().snnqp_events_to_frames(None, None, 1, 1, 32, 1, None, 0, None, None)
+  rc = _lib.lib().snnqp_events_to_frames(None, None, 1, 1, 32, 1, 0, None, 0, None, None)
   assert rc != 0 and b"null pointer" in _lib.lib().snnqp_last_error()
 
 

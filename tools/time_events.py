@@ -12,7 +12,7 @@ addrs = torch.stack([torch.randint(0, wh, (B * N,), device="cuda", generator=g, 
                      torch.randint(0, 2, (B * N,), device="cuda", generator=g, dtype=torch.int32)], 1).contiguous()
 off = (torch.arange(B + 1, device="cuda", dtype=torch.int64) * N)
 out = torch.empty((B, T, wh, wh, 2), device="cuda", dtype=torch.uint8)
-fn = lambda: ip.events_to_frames(addrs, off, T, wh, 1, out=out)
+fn = lambda: ip.events_to_frames(addrs, off, T, wh, 1, out=out, max_events_per_sample=N)
 for _ in range(3): fn()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 n = 10
