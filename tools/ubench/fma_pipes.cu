@@ -18,7 +18,7 @@ constexpr int R = 2000;
 //       4 setp+selp x16 | 5 16 FFMA + 8 FSET | 6 8 FFMA2 + 8 FSET | 7 8 scalar + 4 packed + 8 FSET
 //       8 LIF scalar-exact (fma,sub,fma,fset,fma) x16 neurons  | 9 same fully packed | 10 same half/half
 template <int MODE>
-__global__ void k(float *out, long long *cyc, float seed) {
+__global__ void __launch_bounds__(640, 1) k(float *out, long long *cyc, float seed) {
   float x[16];
   uint64_t p[8];
 #pragma unroll
@@ -99,6 +99,152 @@ __global__ void k(float *out, long long *cyc, float seed) {
       }
     }
   }
+  if (MODE >= 11 && MODE <= 13) {
+    // 32 neurons per thread = 4 quad positions x 8 quads (4 packed pairs each), like k_conv1_umma<true,16>
+    uint64_t u[4][4];
+    float av[4][8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { u[j][q] = p[(j * 4 + q) & 7]; av[j][2 * q] = x[(j * 4 + q) & 15]; av[j][2 * q + 1] = x[(j * 3 + q) & 15]; }
+    uint8_t *y = reinterpret_cast<uint8_t *>(out) + (size_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 4096 + (threadIdx.x & 31);
+    constexpr size_t ystride = 128;
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t w0[4], w1[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint64_t v = fma2(pack2(av[j][2 * q], av[j][2 * q + 1]), a2, b2);
+          uint64_t un;
+          if (MODE == 11 || MODE == 13) {
+            uint64_t d; asm volatile("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(v), "l"(u[j][q]));
+            un = fma2(d, h2, u[j][q]);
+          } else {
+            un = fma2(u[j][q], h2, v);
+          }
+          float u0, u1; unpack2(un, u0, u1);
+          const float s0 = fset(u0), s1 = fset(u1);
+          u[j][q] = fma2(pack2(-s0, -s1), un, un);
+          w0[j] = __float_as_uint(s0); w1[j] = __float_as_uint(s1);
+        }
+        if (MODE != 13) {
+          y[(2 * q) * ystride] = (uint8_t)(((w0[0] | w0[1]) | (w0[2] | w0[3])) >> 29);
+          y[(2 * q + 1) * ystride] = (uint8_t)(((w1[0] | w1[1]) | (w1[2] | w1[3])) >> 29);
+        } else {
+          x[q] += __uint_as_float((w0[0] | w0[1]) | (w0[2] | w0[3])) + __uint_as_float((w1[0] | w1[1]) | (w1[2] | w1[3]));
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) p[(j + q) & 7] ^= u[j][q];
+  }
+  if (MODE >= 14 && MODE <= 17) {
+    // scaled-domain single-rounding LIF: W_t = fma(W_{t-1}, keep_{t-1}, V_t), keep_t = (W_t < 2^(t+1))
+    // MODE 14: keep by FSET, pool by LOP3 + SHF | 15: keep by scalar FFMA.SAT, pool by LOP3 + SHF
+    // MODE 16: keep by FSET, pool on the FMA pipe (product, low-byte trick) | 17: FFMA.SAT + FMA-pipe pool
+    constexpr bool SAT = (MODE == 15 || MODE == 17), FPOOL = (MODE == 16 || MODE == 17);
+    uint64_t w[4][4], kp[4][4];
+    float av[4][8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { w[j][q] = p[(j * 4 + q) & 7]; kp[j][q] = pack2(1.f, 1.f); av[j][2 * q] = x[(j * 4 + q) & 15]; av[j][2 * q + 1] = x[(j * 3 + q) & 15]; }
+    uint8_t *y = reinterpret_cast<uint8_t *>(out) + (size_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 4096 + (threadIdx.x & 31);
+    float sct = a, bit = b, tht = 2.0f, big = 1e20f;
+    const uint64_t eps2 = pack2(-1.1920929e-7f, -1.1920929e-7f), one2 = pack2(1.0f + 1.1920929e-7f, 1.0f + 1.1920929e-7f);
+    for (int r = 0; r < R; ++r) {
+      const uint64_t sc2 = pack2(sct, sct), bi2 = pack2(bit, bit);
+      const float nbig = -big, bth = big * tht;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint64_t kk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint64_t v = fma2(pack2(av[j][2 * q], av[j][2 * q + 1]), sc2, bi2);
+          const uint64_t wn = fma2(w[j][q], kp[j][q], v);
+          float u0, u1; unpack2(wn, u0, u1);
+          float s0, s1;
+          if (SAT) {
+            asm volatile("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(s0) : "f"(u0), "f"(nbig), "f"(bth));
+            asm volatile("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(s1) : "f"(u1), "f"(nbig), "f"(bth));
+          } else {
+            asm volatile("set.lt.f32.f32 %0, %1, %2;" : "=f"(s0) : "f"(u0), "f"(tht));
+            asm volatile("set.lt.f32.f32 %0, %1, %2;" : "=f"(s1) : "f"(u1), "f"(tht));
+          }
+          w[j][q] = wn; kk[j] = kp[j][q] = pack2(s0, s1);
+        }
+        if (FPOOL) {
+          uint64_t pr;
+          asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(pr) : "l"(kk[0]), "l"(kk[1]));
+          asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(pr) : "l"(pr), "l"(kk[2]));
+          asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(pr) : "l"(pr), "l"(kk[3]));
+          uint64_t z;
+          z = fma2(pr, eps2, one2);
+          float z0, z1; unpack2(z, z0, z1);
+          y[(2 * q) * 128] = (uint8_t)__float_as_uint(z0);
+          y[(2 * q + 1) * 128] = (uint8_t)__float_as_uint(z1);
+        } else {
+          float a0[4], a1[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) unpack2(kk[j], a0[j], a1[j]);
+          y[(2 * q) * 128] = (uint8_t)((((__float_as_uint(a0[0]) & __float_as_uint(a0[1]) & __float_as_uint(a0[2])) & __float_as_uint(a0[3])) ^ 0x3F800000u) >> 29);
+          y[(2 * q + 1) * 128] = (uint8_t)((((__float_as_uint(a1[0]) & __float_as_uint(a1[1]) & __float_as_uint(a1[2])) & __float_as_uint(a1[3])) ^ 0x3F800000u) >> 29);
+        }
+      }
+      sct *= 1.0001f; bit *= 1.0001f; tht *= 1.0001f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) p[(j + q) & 7] ^= w[j][q] ^ kp[j][q];
+  }
+  if (MODE == 18) {
+    uint64_t wb[4][4];
+    float av[4][8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { wb[j][q] = p[(j * 4 + q) & 7]; av[j][2 * q] = x[(j * 4 + q) & 15]; av[j][2 * q + 1] = x[(j * 3 + q) & 15]; }
+    uint8_t *y = reinterpret_cast<uint8_t *>(out) + (size_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 4096 + (threadIdx.x & 31);
+    float sct = a, bit = b, big = 1e20f, tht = 2.0f;
+    const uint64_t eps2 = pack2(-1.1920929e-7f, -1.1920929e-7f), one2 = pack2(1.0f + 1.1920929e-7f, 1.0f + 1.1920929e-7f);
+    for (int r = 0; r < R; ++r) {
+      const uint64_t sc2 = pack2(sct, sct);
+      bit *= 1.0001f;
+      const uint64_t bn2 = pack2(bit, bit);
+      const float nbig = -big, bth = big * tht;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint64_t kk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint64_t wn = fma2(pack2(av[j][2 * q], av[j][2 * q + 1]), sc2, wb[j][q]);
+          float u0, u1; unpack2(wn, u0, u1);
+          float s0, s1;
+          asm volatile("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(s0) : "f"(u0), "f"(nbig), "f"(bth));
+          asm volatile("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(s1) : "f"(u1), "f"(nbig), "f"(bth));
+          kk[j] = pack2(s0, s1);
+          wb[j][q] = fma2(wn, kk[j], bn2);
+        }
+        uint64_t pr;
+        asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(pr) : "l"(kk[0]), "l"(kk[1]));
+        asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(pr) : "l"(pr), "l"(kk[2]));
+        asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(pr) : "l"(pr), "l"(kk[3]));
+        const uint64_t z = fma2(pr, eps2, one2);
+        float z0, z1; unpack2(z, z0, z1);
+        y[(2 * q) * 128] = (uint8_t)__float_as_uint(z0);
+        y[(2 * q + 1) * 128] = (uint8_t)__float_as_uint(z1);
+      }
+      sct *= 1.0001f; tht *= 1.0001f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) p[(j + q) & 7] ^= wb[j][q];
+  }
   const long long t1 = clock64();
   float acc = 0;
 #pragma unroll
@@ -124,7 +270,7 @@ void run(const char *name, int slots, float *out, long long *cyc) {
 
 int main() {
   float *out; long long *cyc;
-  cudaMalloc(&out, 148 * 512 * 4); cudaMalloc(&cyc, 8);
+  cudaMalloc(&out, (size_t)148 * 512 * 2048 + (1 << 20)); cudaMalloc(&cyc, 8);
   run<0>("16 scalar FFMA", 16, out, cyc);
   run<1>("8 FFMA2 (=16 lane-ops)", 16, out, cyc);
   run<2>("8 scalar FFMA + 4 FFMA2 (=16 lane-ops)", 16, out, cyc);
@@ -136,5 +282,13 @@ int main() {
   run<8>("LIF exact scalar x16 neurons", 16, out, cyc);
   run<9>("LIF exact packed x16 neurons", 16, out, cyc);
   run<10>("LIF exact half packed/half scalar x16", 16, out, cyc);
+  run<11>("conv1 epilogue step (32 neurons, exact, OR-pool, STG.U8)", 32, out, cyc);
+  run<12>("conv1 epilogue step (32 neurons, single-rounding form)", 32, out, cyc);
+  run<13>("conv1 epilogue step (32 neurons, exact, no stores)", 32, out, cyc);
+  run<14>("scaled 3-op LIF: FSET keep, LOP3 pool", 32, out, cyc);
+  run<15>("scaled 3-op LIF: FFMA.SAT keep, LOP3 pool", 32, out, cyc);
+  run<16>("scaled 3-op LIF: FSET keep, FMA-pipe pool", 32, out, cyc);
+  run<17>("scaled 3-op LIF: FFMA.SAT keep, FMA-pipe pool", 32, out, cyc);
+  run<18>("scaled 3-op LIF, one state register (bias folded)", 32, out, cyc);
   return 0;
 }
