@@ -47,53 +47,52 @@ def peaks():
 
 
 class ClockSampler:
-  Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-       "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-       "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+  """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line) through NVML
+  (nvidia_ml_py) from a background thread every 10 ms -- nvidia-smi -lms block-buffers its output and loses the
+  samples of a sub-second region when it is stopped."""
 
   def __init__(self, gpu_index: int):
     self.idx = gpu_index
-    self.proc = None
-    self.path = f"/tmp/snnqp_clocks_{os.getpid()}.csv"
+    self.samples = []
+    self.thread = None
+    self.stop_flag = False
+
+  def _run(self):
+    import pynvml as N
+    try:
+      N.nvmlInit()
+      h = N.nvmlDeviceGetHandleByIndex(self.idx)
+      mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+      while not self.stop_flag:
+        sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+        try:
+          r = N.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+          r = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        self.samples.append((sm, mx, int(r)))
+        time.sleep(0.01)
+    except Exception as e:          # no NVML: report no samples rather than fail the bench
+      self.err = repr(e)
 
   def start(self):
-    try:
-      self.f = open(self.path, "w")
-      self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                    "-lms", "100", "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
-    except Exception:
-      self.proc = None
+    import threading
+    self.stop_flag = False
+    self.thread = threading.Thread(target=self._run, daemon=True)
+    self.thread.start()
 
   def stop(self):
-    out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-    if self.proc is None:
+    out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    if self.thread is None:
       return out
-    self.proc.terminate()
-    try:
-      self.proc.wait(5)
-    except Exception:
-      self.proc.kill()
-    self.f.close()
-    sm, mx, reasons = [], [], set()
-    for line in open(self.path):
-      parts = [x.strip() for x in line.split(",")]
-      if len(parts) < 9:
-        continue
-      try:
-        sm.append(float(parts[1])); mx.append(float(parts[2]))
-      except ValueError:
-        continue
-      for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
-        if val.lower().startswith("active"):
-          reasons.add(name)
-    if sm:
-      out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-             "samples": len(sm)}
-    try:
-      os.remove(self.path)
-    except OSError:
-      pass
-    return out
+    self.stop_flag = True
+    self.thread.join(2)
+    if not self.samples:
+      return out
+    bits = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4,
+            "hw_power_brake_slowdown": 0x80}
+    reasons = sorted({name for _, _, r in self.samples for name, b in bits.items() if r & b})
+    return {"sm_mhz": statistics.median([x[0] for x in self.samples]), "sm_max_mhz": max(x[1] for x in self.samples),
+            "reasons": reasons, "samples": len(self.samples)}
 
 
 def cpu_reference_samples_per_s(bits, prune, T, H, sample_B, reps, threads):
@@ -250,8 +249,10 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "int8 x {0,1}/u8 -> int32 accumulate, fp32 epilogue", "data": "synthetic",
-        "config": workload_config(args, B, ws),
+        "dtype": "int8", "data": "synthetic",
+        "config": dict(workload_config(args, B, ws),
+                       arithmetic="int8 weights x u8 spikes/counts -> int32 accumulate (tcgen05 kind::i8; conv1 as exact "
+                                  "kind::f16), fp32 dequant + BatchNorm + LIF epilogue"),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_frames.numel()) * ws,
                 "d2h_bytes_per_step": int(host_logits.numel() * 4) * ws, "steps": e2e_steps},
         "gpu_launches": launches,
@@ -334,7 +335,7 @@ def dominant_kernel_roofline(eng, frames, args, dev):
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
-  ap.add_argument("--steps", type=int, default=5)
+  ap.add_argument("--steps", type=int, default=20)
   ap.add_argument("--warmup", type=int, default=3)
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
   ap.add_argument("--kernels", default="auto", choices=["auto", "simt", "tcgen05"])
