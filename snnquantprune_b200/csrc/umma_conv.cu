@@ -467,8 +467,8 @@ int launch_conv3x3_umma(const snnqp_block_params &p, const uint8_t *x, const int
   a.tb_swapped = tb_swapped ? 1 : 0;
   a.one = 1;
   a.base_off_mode = 0;   // the hardware applies the 128B swizzle on absolute smem address bits (measured)
-  const char *dbg = getenv("SNNQP_UMMA_DEBUG");
-  a.debug = dbg ? atoi(dbg) : 0;
+  static const int dbg_env = getenv("SNNQP_UMMA_DEBUG") ? atoi(getenv("SNNQP_UMMA_DEBUG")) : 0;   // bisection switches (tools/)
+  a.debug = dbg_env;
   a.stage_tx_bytes = (uint32_t)((TH + 2) * P * kC);
   a.scale = scale; a.bias = bias;
   a.slab_nz = reinterpret_cast<const uint8_t *>(wq) + kWBytes;   // blob tail written by snnqp_pack_conv3x3

@@ -460,8 +460,8 @@ int launch_conv1_umma(const snnqp_block_params &p, const uint8_t *x, const int8_
   a.y_stride_t = p.y_stride_t; a.y_stride_b = p.y_stride_b;
   a.tau = p.tau; a.v_th = p.v_threshold; a.v_reset = p.v_reset;
   a.pool = p.pool; a.tb_swapped = swapped ? 1 : 0;
-  const char *dbg = getenv("SNNQP_C1_DEBUG");
-  a.debug = dbg ? atoi(dbg) : 0;
+  static const int dbg_env = getenv("SNNQP_C1_DEBUG") ? atoi(getenv("SNNQP_C1_DEBUG")) : 0;   // bisection switches (tools/)
+  a.debug = dbg_env;
   a.wq4 = wq4; a.scale = scale; a.bias = bias;
   a.spikes = spikes; a.u_final = u_final; a.acc_dump = acc_dump;
   const int grid = a.total_items < sm_count() ? a.total_items : sm_count();
