@@ -382,6 +382,104 @@ k_tcja_att(const snnqp_block_params p, const int32_t *__restrict__ counts,
   }
 }
 
+// Same result (integer accumulators are exact in any order), dp4a form for C == 128, T <= 32: the conv_c weights
+// are re-laid in shared memory as [j][c/4][c'] words (4 input channels per word), the counts as two byte planes
+// (low byte, high byte: counts <= H*W <= 65535), so that 4 multiply-adds cost one dp4a per plane instead of
+// two shared-memory loads and an IMAD each, and a weight word is loaded once for all of a thread's timesteps.
+// HIGH == false when H*W <= 255 (the high plane is all zero).
+template <bool HIGH>
+__global__ void __launch_bounds__(256)
+k_tcja_att_dp4a(const snnqp_block_params p, const int32_t *__restrict__ counts,
+                const int8_t *__restrict__ wq_t, const int8_t *__restrict__ wq_c,
+                const float *__restrict__ scale_t, const float *__restrict__ scale_c,
+                float *__restrict__ att) {
+  constexpr int C = 128, C4 = C / 4, NT = 16;                               // NT: timesteps per thread (T <= 32)
+  extern __shared__ __align__(16) uint8_t tcja_smem[];
+  const int b = blockIdx.x, T = p.T;
+  uint32_t *qc4 = reinterpret_cast<uint32_t *>(tcja_smem);                  // [4][C4][C] words
+  int32_t *cnt = reinterpret_cast<int32_t *>(qc4 + 4 * C4 * C);             // [T][C]
+  uint32_t *lo4 = reinterpret_cast<uint32_t *>(cnt + T * C);                // [T + 3][C4], rows -1 and T, T+1 zero
+  uint32_t *hi4 = lo4 + (T + 3) * C4;
+  int8_t *qt = reinterpret_cast<int8_t *>(hi4 + (T + 3) * C4);              // [4][T][T]
+  // weights: global [j][ci][c'] bytes -> words {ci, ci+1, ci+2, ci+3} at [j][ci/4][c']: four 16-byte row pieces
+  // (rows ci .. ci+3, 16 consecutive c') are transposed in registers into 16 words
+  for (int d = threadIdx.x; d < 4 * C4 * (C / 16); d += blockDim.x) {
+    const int c16 = d % (C / 16), ci4 = (d / (C / 16)) % C4, j = d / ((C / 16) * C4);
+    const int4 *src = reinterpret_cast<const int4 *>(wq_c + ((size_t)j * C + 4 * ci4) * C + 16 * c16);
+    const int4 r0 = __ldg(src), r1 = __ldg(src + C / 16), r2 = __ldg(src + 2 * (C / 16)), r3 = __ldg(src + 3 * (C / 16));
+    uint4 *dst = reinterpret_cast<uint4 *>(qc4 + (j * C4 + ci4) * C + 16 * c16);
+    auto tr = [](uint32_t a, uint32_t b, uint32_t c, uint32_t e) {           // 4 x 4 byte transpose
+      const uint32_t t0 = __byte_perm(a, b, 0x5140), t1 = __byte_perm(c, e, 0x5140);   // (a0 b0 a1 b1), (c0 e0 c1 e1)
+      const uint32_t t2 = __byte_perm(a, b, 0x7362), t3 = __byte_perm(c, e, 0x7362);   // (a2 b2 a3 b3), (c2 e2 c3 e3)
+      return make_uint4(__byte_perm(t0, t1, 0x5410), __byte_perm(t0, t1, 0x7632), __byte_perm(t2, t3, 0x5410),
+                        __byte_perm(t2, t3, 0x7632));
+    };
+    dst[0] = tr((uint32_t)r0.x, (uint32_t)r1.x, (uint32_t)r2.x, (uint32_t)r3.x);
+    dst[1] = tr((uint32_t)r0.y, (uint32_t)r1.y, (uint32_t)r2.y, (uint32_t)r3.y);
+    dst[2] = tr((uint32_t)r0.z, (uint32_t)r1.z, (uint32_t)r2.z, (uint32_t)r3.z);
+    dst[3] = tr((uint32_t)r0.w, (uint32_t)r1.w, (uint32_t)r2.w, (uint32_t)r3.w);
+  }
+  for (int d = threadIdx.x; d < T * C; d += blockDim.x) cnt[d] = counts[(int64_t)b * T * C + d];
+  for (int d = threadIdx.x; d < (T + 3) * C4; d += blockDim.x) {
+    const int tt = d / C4 - 1, c4 = d % C4;                                  // padded row index -> timestep
+    uint32_t l = 0, h = 0;
+    if (tt >= 0 && tt < T) {
+      const int4 v = *reinterpret_cast<const int4 *>(counts + ((int64_t)b * T + tt) * C + 4 * c4);
+      l = (v.x & 255) | ((v.y & 255) << 8) | ((v.z & 255) << 16) | ((uint32_t)(v.w & 255) << 24);
+      h = ((v.x >> 8) & 255) | (((v.y >> 8) & 255) << 8) | (((v.z >> 8) & 255) << 16) | ((uint32_t)((v.w >> 8) & 255) << 24);
+    }
+    lo4[d] = l;
+    hi4[d] = h;
+  }
+  for (int d = threadIdx.x; d < 4 * T * T; d += blockDim.x) qt[d] = wq_t[d];
+  __syncthreads();
+  const float st = *scale_t, scc = *scale_c;
+  const int c = threadIdx.x % C, part = threadIdx.x / C;                     // blockDim.x == 2 * C
+  int accl[NT], acch[NT];
+#pragma unroll
+  for (int i = 0; i < NT; ++i) { accl[i] = 0; acch[i] = 0; }
+  for (int ci16 = 0; ci16 < C4 / 4; ++ci16) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) w[k] = (int)qc4[(j * C4 + 4 * ci16 + k) * C + c];
+#pragma unroll
+      for (int i = 0; i < NT; ++i) {
+        const int t = part + 2 * i;
+        if (t < T) {
+          // padded row (t + j - 1) + 1 = t + j; 'SAME' pads (low 1, high 2) read the zero rows
+          const uint4 l = *reinterpret_cast<const uint4 *>(lo4 + (t + j) * C4 + 4 * ci16);
+          accl[i] = dp4a_us(l.x, w[0], accl[i]); accl[i] = dp4a_us(l.y, w[1], accl[i]);
+          accl[i] = dp4a_us(l.z, w[2], accl[i]); accl[i] = dp4a_us(l.w, w[3], accl[i]);
+          if constexpr (HIGH) {
+            const uint4 h = *reinterpret_cast<const uint4 *>(hi4 + (t + j) * C4 + 4 * ci16);
+            acch[i] = dp4a_us(h.x, w[0], acch[i]); acch[i] = dp4a_us(h.y, w[1], acch[i]);
+            acch[i] = dp4a_us(h.z, w[2], acch[i]); acch[i] = dp4a_us(h.w, w[3], acch[i]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NT; ++i) {
+    const int t = part + 2 * i;
+    if (t >= T) continue;
+    const int acc_c = accl[i] + (HIGH ? acch[i] * 256 : 0);
+    int acc_t = 0;
+    for (int j = 0; j < 4; ++j) {
+      const int cc = c + j - 1;
+      if (cc >= 0 && cc < C)
+        for (int ti = 0; ti < T; ++ti) acc_t += cnt[ti * C + cc] * (int)qt[(j * T + ti) * T + t];
+    }
+    const float to = __fmul_rn((float)acc_t, st);
+    const float co = __fmul_rn((float)acc_c, scc);
+    const float pr = __fmul_rn(co, to);
+    const float a = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-pr)));
+    att[(int64_t)t * p.att_stride_t + (int64_t)b * p.att_stride_b + c] = a;
+  }
+}
+
 // 2x2 max-pool on uint8, 4 channels per thread (HBM-bound)
 __global__ void k_maxpool2(const snnqp_block_params p, const uint8_t *__restrict__ x,
                            uint8_t *__restrict__ y) {
@@ -510,6 +608,20 @@ int launch_tcja(const snnqp_block_params &p, const uint8_t *spikes, const int8_t
   if (spikes) {   // else: counts were accumulated by the producing conv block (spike_counts output)
     k_tcja_counts<<<p.T * p.B, 256, 0, st>>>(p, spikes, counts);
     SNNQP_POST_LAUNCH("k_tcja_counts");
+  }
+  if (p.Cin == 128 && p.T <= 32 && (int64_t)p.H * p.W <= 65535 && !(reinterpret_cast<uintptr_t>(counts) & 15) &&
+      !(reinterpret_cast<uintptr_t>(wq_c) & 15)) {
+    const size_t smem4 = (size_t)4 * 128 * 128 + (size_t)p.T * 128 * sizeof(int32_t) + (size_t)2 * (p.T + 3) * 32 * 4 +
+                         (size_t)4 * p.T * p.T + 16;
+    if ((int64_t)p.H * p.W <= 255) {
+      SNNQP_CUDA(cudaFuncSetAttribute(k_tcja_att_dp4a<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+      k_tcja_att_dp4a<false><<<p.B, 256, smem4, st>>>(p, counts, wq_t, wq_c, scale_t, scale_c, att);
+    } else {
+      SNNQP_CUDA(cudaFuncSetAttribute(k_tcja_att_dp4a<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+      k_tcja_att_dp4a<true><<<p.B, 256, smem4, st>>>(p, counts, wq_t, wq_c, scale_t, scale_c, att);
+    }
+    SNNQP_POST_LAUNCH("k_tcja_att_dp4a");
+    return SNNQP_OK;
   }
   const size_t smem = (size_t)4 * p.Cin * p.Cin + (size_t)p.T * p.Cin * sizeof(int32_t) + (size_t)4 * p.T * p.T + 16;
   SNNQP_CUDA(cudaFuncSetAttribute(k_tcja_att, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
