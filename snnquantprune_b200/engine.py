@@ -194,6 +194,18 @@ class CextNetEngine:
     self._run(frames, logits, collect)
     return logits
 
+  def host_chunks(self, B: int, first: int = 16, growth: float = 1.3):
+    """Chunk schedule of the host path: a small first chunk (its copy is the only one nothing overlaps),
+    then sizes growing by ``growth`` -- below the compute/copy time ratio of a chunk, so the copy of chunk
+    k+1 always ends before the head of chunk k does -- up to ``self.chunk`` (few, large launches)."""
+    out, b0, n = [], 0, float(min(first, self.chunk))
+    while b0 < B:
+      m = min(int(n), self.chunk, B - b0)
+      out.append((b0, m))
+      b0 += m
+      n = max(n * growth, n + 1)
+    return out
+
   def forward_host(self, host_frames: torch.Tensor, out_host: Optional[torch.Tensor] = None) -> torch.Tensor:
     """End-to-end call from HOST memory: ``host_frames`` is a (pinned) uint8 CPU tensor
     (B,T,H,W,2).  Chunks are copied host->device on a side stream into two staging buffers
@@ -215,8 +227,7 @@ class CextNetEngine:
     logits = torch.empty((B, pk.num_classes), device=self.device, dtype=torch.float32)
     self._copy_stream.wait_stream(cur)
     done = []
-    for i, b0 in enumerate(range(0, B, Bc)):
-      n = min(Bc, B - b0)
+    for i, (b0, n) in enumerate(self.host_chunks(B)):
       buf = ws["stage"][i & 1][:n]
       if i >= 2:
         self._copy_stream.wait_event(done[i - 2])       # staging buffer free again
