@@ -228,6 +228,9 @@ def run_ours(args):
 
   # ---- dominant kernel (conv2 block), timed live with CUDA events ----------
   roof = dominant_kernel_roofline(eng, frames, args, dev)
+  # per-layer input densities of the synthetic run (a dead network would make the throughput meaningless)
+  eng.forward(frames)
+  rates = {k: round(v["mean"], 4) for k, v in eng.densities(frames).items()}
 
   # ---- final accuracy reduction: the only collective, outside the timed region
   out = torch.zeros(2, device=dev, dtype=torch.float32)
@@ -267,6 +270,7 @@ def run_ours(args):
                              "peak_measured_int8": roof["peak"], "frac_measured_int8": net_tops / roof["peak"],
                              "peaks": pk["src"]},
         "accuracy_vs_random_labels": cnt[0].item() / cnt[2].item(),
+        "mean_nonzero_fraction_of_layer_inputs": rates,
         "kernels": args.kernels,
     }
     sys.stdout.flush()

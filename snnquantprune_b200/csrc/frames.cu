@@ -80,18 +80,19 @@ k_events_to_frames(const int32_t *__restrict__ addrs, const int64_t *__restrict_
 
 // grid: (blocks_per_slice, n_slices); 16 bytes per thread per iteration
 __global__ void __launch_bounds__(256)
-k_slice_nonzeros(const uint8_t *__restrict__ x, int64_t slice_bytes, int64_t stride_slice, int32_t *__restrict__ counts) {
+k_slice_nonzeros(const uint8_t *__restrict__ x, int64_t slice_bytes, int64_t stride_slice, int vec16,
+                 int32_t *__restrict__ counts) {
   const uint8_t *base = x + (int64_t)blockIdx.y * stride_slice;
-  const int64_t n16 = slice_bytes / 16;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n16 = vec16 ? slice_bytes / 16 : 0;           // unaligned slices: byte path only
   int c = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t i = tid; i < n16; i += nthr) {
     const uint4 v = __ldg(reinterpret_cast<const uint4 *>(base) + i);
-    // non-zero bytes of a word: (b | (b + 0x7F..)) bit 7 per byte
+    // non-zero bytes of a word: bit 7 of ((b & 0x7F) + 0x7F) | b, per byte
     auto nzb = [](uint32_t w) { return __popc(((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu | w) & 0x80808080u); };
     c += nzb(v.x) + nzb(v.y) + nzb(v.z) + nzb(v.w);
   }
-  if (blockIdx.x == 0)
-    for (int64_t i = n16 * 16 + threadIdx.x; i < slice_bytes; i += blockDim.x) c += base[i] != 0;
+  for (int64_t i = n16 * 16 + tid; i < slice_bytes; i += nthr) c += base[i] != 0;
   for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(counts + blockIdx.y, c);
 }
@@ -145,12 +146,12 @@ extern "C" int snnqp_slice_nonzeros(const uint8_t *x, int n_slices, int64_t slic
   if (!x || !counts) return invalid("snnqp_slice_nonzeros: null pointer");
   if (n_slices <= 0 || slice_bytes <= 0) return invalid("snnqp_slice_nonzeros: n_slices and slice_bytes must be > 0");
   if (n_slices > 65535) return unsupported("snnqp_slice_nonzeros: more than 65535 slices");
-  if ((reinterpret_cast<uintptr_t>(x) & 15) || (stride_slice & 15)) return invalid("snnqp_slice_nonzeros: x and the slice stride must be 16-byte aligned");
+  const int vec16 = !((reinterpret_cast<uintptr_t>(x) & 15) || (stride_slice & 15));
   SNNQP_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * n_slices, st));
   int bx = (int)((slice_bytes / 16 + 255) / 256);
   const int cap = (8 * sm_count() + n_slices - 1) / n_slices;          // ~8 CTAs per SM over the whole grid
   bx = bx < 1 ? 1 : (bx > cap ? (cap < 1 ? 1 : cap) : bx);
-  k_slice_nonzeros<<<dim3(bx, n_slices), 256, 0, st>>>(x, slice_bytes, stride_slice, counts);
+  k_slice_nonzeros<<<dim3(bx, n_slices), 256, 0, st>>>(x, slice_bytes, stride_slice, vec16, counts);
   SNNQP_POST_LAUNCH("k_slice_nonzeros");
   return SNNQP_OK;
 }

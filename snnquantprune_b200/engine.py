@@ -174,6 +174,27 @@ class CextNetEngine:
       for k in ("s1", "s2", "s3", "p4", "p5", "att4", "att5", "d1", "d2"):
         collect[k] = ws[k].clone()
 
+  def densities(self, frames: Optional[torch.Tensor] = None) -> Dict[str, Dict[str, float]]:
+    """The input densities the reference sows per layer (examples/tcja/models.py:128-142, 'conv_i_inpt_min/mean',
+    'dense*_inpt_*': fraction of non-zeros per (t, b) slice, max ('_min' in the reference's naming) and mean),
+    measured with ``snnqp_slice_nonzeros`` on the tensors the LAST forward left in the workspace -- the pooled
+    spikes that feed the next layer.  ``frames``: also report the input frames.  conv2 / conv3 inputs cover the
+    last head chunk only (they are per-chunk buffers).  Host sync (it returns Python floats)."""
+    from .input_pipeline import density_stats
+    if not self._ws:
+      raise RuntimeError("densities() needs a forward first")
+    ws = list(self._ws.values())[-1]
+    T = self.pk.T
+    named = {"conv_1_inpt": ws["s1"], "conv_2_inpt": ws["s2"], "conv_3_inpt": ws["s3"], "conv_t_0_inpt": ws["p4"],
+             "dense1_inpt": ws["p5"], "dense2_inpt": ws["d1"], "dense2_out": ws["d2"]}
+    if frames is not None:
+      named = dict(conv_0_inpt=frames, **named)
+    out = {}
+    for k, x in named.items():
+      d = density_stats(x, x.shape[0] * T)
+      out[k] = {"min": float(d["min"]), "mean": float(d["mean"])}
+    return out
+
   def _check(self, frames: torch.Tensor) -> None:
     if not frames.is_cuda or frames.dtype != torch.uint8:
       raise ValueError("frames must be a uint8 CUDA tensor (B,T,H,W,2); no CPU fallback")

@@ -98,7 +98,7 @@ def test_events_feed_the_hot_path(cuda_lib):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape", [(4, 3, 16, 16, 128), (2, 5, 7, 16), (20, 2, 64, 64, 128)])
+@pytest.mark.parametrize("shape", [(4, 3, 16, 16, 128), (2, 5, 7, 16), (20, 2, 64, 64, 128), (3, 4, 110), (2, 2, 5)])
 def test_density_stats_bit_exact(cuda_lib, shape):
   from snnquantprune_b200 import input_pipeline as ip
   rng = np.random.default_rng(len(shape))
@@ -107,3 +107,21 @@ def test_density_stats_bit_exact(cuda_lib, shape):
   w = ref_events.sow_densities(x)
   assert np.array_equal(d["counts"].cpu().numpy().reshape(shape[:2]), w["counts"])
   assert abs(d["min"].item() - w["min"]) < 1e-12 and abs(d["mean"].item() - w["mean"]) < 1e-12
+
+
+@pytest.mark.gpu
+def test_engine_densities_match_oracle(cuda_lib):
+  """CextNetEngine.densities() == the reference's sowed input densities computed by the oracle on the same tensors."""
+  from snnquantprune_b200 import CextNetEngine, pack_cextnet, synthetic
+  bits, T, H, B = 8, 4, 32, 3
+  v = synthetic.make_variables(bits=bits, prune_percentage=0.5, T=T, H=H, seed=1)
+  fr = torch.as_tensor(synthetic.make_frames(B, T, H, H, seed=2)).cuda()
+  eng = CextNetEngine(pack_cextnet(v, bits, T, H, device="cuda"))
+  c = {}
+  eng.forward(fr, collect=c)
+  d = eng.densities(fr)
+  for key, name in (("conv_0_inpt", None), ("conv_1_inpt", "s1"), ("conv_3_inpt", "s3"), ("dense2_inpt", "d1")):
+    x = fr.cpu().numpy() if name is None else c[name].cpu().numpy()
+    w = ref_events.sow_densities(np.swapaxes(x, 0, 1))             # (T, B, ...)
+    assert abs(d[key]["min"] - w["min"]) < 1e-12 and abs(d[key]["mean"] - w["mean"]) < 1e-12, key
+  assert 0.0 < d["conv_1_inpt"]["mean"] < 1.0
