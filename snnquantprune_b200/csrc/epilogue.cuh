@@ -29,16 +29,6 @@ struct LifParams {
   }
 };
 
-// int32 accumulator -> fp32 on the FMA pipe: as_float(acc * one + 0x4B400000) - 1.5 * 2^23 (IMAD + FADD), exact
-// for |acc| < 2^22.  `one` is a runtime 1 so that ptxas keeps the IMAD instead of folding it to an ALU-pipe
-// IADD3.  ncu: with I2FP the half-rate ALU pipe (I2FP + FSETP + FSEL) is the epilogue's bottleneck (79 % busy
-// vs 29 % for the FMA pipe); this moves 2 of its ~7.5 cycles per neuron over.
-__device__ __forceinline__ float cvt_acc_fma_pipe(uint32_t acc, int one) {
-  uint32_t m;
-  asm("mad.lo.s32 %0, %1, %2, 0x4B400000;" : "=r"(m) : "r"(acc), "r"(one));
-  return __fadd_rn(__uint_as_float(m), -12582912.0f);
-}
-
 __device__ __forceinline__ bool lif_is_std(float tau, float v_th, float v_reset) {
   return tau == 2.0f && v_th == 1.0f && v_reset == 0.0f;
 }
@@ -107,24 +97,6 @@ __device__ __forceinline__ uint64_t lif2_std(uint64_t &u2, uint32_t acc0, uint32
   unpack2(un, a, b);
   const float s0 = a >= 1.0f ? 1.0f : 0.0f, s1 = b >= 1.0f ? 1.0f : 0.0f;
   u2 = fma2(pack2(-s0, -s1), un, un);
-  return pack2(s0, s1);
-}
-
-// Same for accumulators that already are fp32 (kind::f16 contraction): no conversion at all.
-// f0/f1 should be adjacent registers of one tcgen05.ld so that the pack is a free register pair.
-// Measured: FFMA2 / FADD2 run at half the lane rate of scalar FFMA (one of the two FMA sub-pipes), so a fully
-// packed form only trades issue slots for FMA-pipe cycles.  Mixed form: the two FMAs packed, the subtraction
-// and the reset scalar -- loads issue port, both FMA sub-pipes and the ALU pipe about evenly.
-__device__ __forceinline__ uint64_t lif2_std_f32(uint64_t &u2, uint32_t f0, uint32_t f1, const Lif2Consts &k) {
-  const uint64_t v = fma2(pack2(__uint_as_float(f0), __uint_as_float(f1)), k.sc2, k.bi2);
-  float v0, v1, u0, u1;
-  unpack2(v, v0, v1);
-  unpack2(u2, u0, u1);
-  const uint64_t un = fma2(pack2(__fsub_rn(v0, u0), __fsub_rn(v1, u1)), k.half2, u2);
-  float a, b;
-  unpack2(un, a, b);
-  const float s0 = a >= 1.0f ? 1.0f : 0.0f, s1 = b >= 1.0f ? 1.0f : 0.0f;
-  u2 = pack2(__fmaf_rn(-s0, a, a), __fmaf_rn(-s1, b, b));
   return pack2(s0, s1);
 }
 
