@@ -350,7 +350,7 @@ def main():
   ap.add_argument("--T", type=int, default=20)
   ap.add_argument("--H", type=int, default=128)
   ap.add_argument("--e2e-steps", type=int, default=5)
-  ap.add_argument("--e2e-chunk", type=int, default=128, help="largest H2D / head chunk of the end-to-end path (chunks grow from 16)")
+  ap.add_argument("--e2e-chunk", type=int, default=256, help="largest H2D / head chunk of the end-to-end path (chunks grow from 16)")
   ap.add_argument("--cpu-batch", type=int, default=8)
   ap.add_argument("--ref-batch", type=int, default=8)
   ap.add_argument("--no-cpu-baseline", action="store_true")

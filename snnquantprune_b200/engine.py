@@ -215,10 +215,11 @@ class CextNetEngine:
     self._run(frames, logits, collect)
     return logits
 
-  def host_chunks(self, B: int, first: int = 16, growth: float = 1.3):
+  def host_chunks(self, B: int, first: int = 16, growth: float = 1.5):
     """Chunk schedule of the host path: a small first chunk (its copy is the only one nothing overlaps),
-    then sizes growing by ``growth`` -- below the compute/copy time ratio of a chunk, so the copy of chunk
-    k+1 always ends before the head of chunk k does -- up to ``self.chunk`` (few, large launches)."""
+    then sizes growing by ``growth`` -- about the compute/copy time ratio of a chunk, so the copy of chunk
+    k+1 ends roughly when the head of chunk k does -- up to ``self.chunk`` (few, large launches; measured best
+    at 1.5 with a cap of 256: tools/time_e2e.py)."""
     out, b0, n = [], 0, float(min(first, self.chunk))
     while b0 < B:
       m = min(int(n), self.chunk, B - b0)

@@ -9,7 +9,7 @@ v = synthetic.make_variables(bits=8, prune_percentage=0.5, T=T, H=H, seed=1)
 pk = pack_cextnet(v, 8, T, H)
 host = torch.as_tensor(synthetic.make_frames(B, T, H, H, seed=0)).pin_memory()
 out = torch.empty((B, 11), dtype=torch.float32).pin_memory()
-for cap, first, growth in [(32, 32, 1.0), (64, 16, 1.3), (128, 16, 1.3), (128, 16, 1.2), (128, 8, 1.3), (128, 24, 1.25), (256, 16, 1.3), (256, 16, 1.2), (96, 16, 1.3)]:
+for cap, first, growth in [(128, 16, 1.3), (256, 16, 1.5), (256, 16, 2.0), (256, 32, 1.5), (256, 24, 1.7), (256, 8, 2.0), (256, 64, 1.3)]:
   eng = CextNetEngine(pk, chunk=cap)
   sched = eng.host_chunks(B, first, growth)
   eng.host_chunks = lambda B_, s=sched: s
