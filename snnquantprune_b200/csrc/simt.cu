@@ -6,6 +6,8 @@
 // (umma_conv.cu).  Each kernel keeps the T loop inside, so membrane potentials
 // live in registers and never touch HBM between timesteps
 // (reference SpikingBlock scan: spiking_learning.py:441-472).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace snnqp {
@@ -480,6 +482,131 @@ k_tcja_att_dp4a(const snnqp_block_params p, const int32_t *__restrict__ counts,
   }
 }
 
+// Tensor-core form of the same arithmetic for C == 128, T <= 32 (legacy mma.sync m16n8k32 u8 x s8 -> s32; the
+// GEMM is tiny -- [T x 512] x [512 x 128] per sample -- and latency-bound, not worth a tcgen05 pipeline):
+//   c_out accumulators D[t][c'] = sum_{j, ci} cnt[t + j - 1][ci] * q_c[j][ci][c'] with the counts as u8 byte planes
+//   (low, high; the high plane is skipped when the sample has no count >= 256), one block per sample,
+//   warp w owns output channels 16w .. 16w+15 and both 16-row time tiles.
+//   t_out (80 multiply-adds per output) stays scalar and goes through shared memory.
+// Integer accumulators: bit-identical to k_tcja_att / k_tcja_att_dp4a.  Shared-memory row strides are padded
+// (36 / 136 words) so that the fragment loads of a warp hit 32 different banks.
+__global__ void __launch_bounds__(256)
+k_tcja_att_mma(const snnqp_block_params p, const int32_t *__restrict__ counts,
+               const int8_t *__restrict__ wq_t, const int8_t *__restrict__ wq_c,
+               const float *__restrict__ scale_t, const float *__restrict__ scale_c,
+               float *__restrict__ att) {
+  constexpr int C = 128, C4 = C / 4, SA = C4 + 4, SB = C + 8, ROWS = 36;    // ROWS: padded time rows (-1 .. 34)
+  extern __shared__ __align__(16) uint8_t tcja_smem[];
+  const int b = blockIdx.x, T = p.T;
+  uint32_t *qc4 = reinterpret_cast<uint32_t *>(tcja_smem);                  // [4][C4][SB] words
+  uint32_t *lo4 = qc4 + 4 * C4 * SB;                                        // [ROWS][SA]
+  uint32_t *hi4 = lo4 + ROWS * SA;                                          // [ROWS][SA]
+  int32_t *cnt = reinterpret_cast<int32_t *>(hi4 + ROWS * SA);              // [T][C]
+  int32_t *tout = cnt + T * C;                                              // [T][C] t_out accumulators
+  int8_t *qt = reinterpret_cast<int8_t *>(tout + T * C);                    // [4][T][T]
+  for (int d = threadIdx.x; d < 4 * C4 * (C / 16); d += blockDim.x) {
+    const int c16 = d % (C / 16), ci4 = (d / (C / 16)) % C4, j = d / ((C / 16) * C4);
+    const int4 *src = reinterpret_cast<const int4 *>(wq_c + ((size_t)j * C + 4 * ci4) * C + 16 * c16);
+    const int4 r0 = __ldg(src), r1 = __ldg(src + C / 16), r2 = __ldg(src + 2 * (C / 16)), r3 = __ldg(src + 3 * (C / 16));
+    uint4 *dst = reinterpret_cast<uint4 *>(qc4 + (j * C4 + ci4) * SB + 16 * c16);
+    auto tr = [](uint32_t a, uint32_t b2, uint32_t c, uint32_t e) {          // 4 x 4 byte transpose
+      const uint32_t t0 = __byte_perm(a, b2, 0x5140), t1 = __byte_perm(c, e, 0x5140);
+      const uint32_t t2 = __byte_perm(a, b2, 0x7362), t3 = __byte_perm(c, e, 0x7362);
+      return make_uint4(__byte_perm(t0, t1, 0x5410), __byte_perm(t0, t1, 0x7632), __byte_perm(t2, t3, 0x5410),
+                        __byte_perm(t2, t3, 0x7632));
+    };
+    dst[0] = tr((uint32_t)r0.x, (uint32_t)r1.x, (uint32_t)r2.x, (uint32_t)r3.x);
+    dst[1] = tr((uint32_t)r0.y, (uint32_t)r1.y, (uint32_t)r2.y, (uint32_t)r3.y);
+    dst[2] = tr((uint32_t)r0.z, (uint32_t)r1.z, (uint32_t)r2.z, (uint32_t)r3.z);
+    dst[3] = tr((uint32_t)r0.w, (uint32_t)r1.w, (uint32_t)r2.w, (uint32_t)r3.w);
+  }
+  for (int d = threadIdx.x; d < T * C; d += blockDim.x) cnt[d] = counts[(int64_t)b * T * C + d];
+  int any_hi = 0;
+  for (int d = threadIdx.x; d < ROWS * C4; d += blockDim.x) {
+    const int tt = d / C4 - 1, c4 = d % C4;                                  // padded row index -> timestep
+    uint32_t l = 0, h = 0;
+    if (tt >= 0 && tt < T) {
+      const int4 v = *reinterpret_cast<const int4 *>(counts + ((int64_t)b * T + tt) * C + 4 * c4);
+      l = (v.x & 255) | ((v.y & 255) << 8) | ((v.z & 255) << 16) | ((uint32_t)(v.w & 255) << 24);
+      h = ((v.x >> 8) & 255) | (((v.y >> 8) & 255) << 8) | (((v.z >> 8) & 255) << 16) | ((uint32_t)((v.w >> 8) & 255) << 24);
+    }
+    lo4[(tt + 1) * SA + c4] = l;
+    hi4[(tt + 1) * SA + c4] = h;
+    any_hi |= (h != 0);
+  }
+  for (int d = threadIdx.x; d < 4 * T * T; d += blockDim.x) qt[d] = wq_t[d];
+  any_hi = __syncthreads_or(any_hi);
+  // ---- t_out[t'][c] = sum_{j, t} cnt[t][c + j - 1] * q_t[j][t][t'] (scalar, 4T multiply-adds each)
+  for (int o = threadIdx.x; o < T * C; o += blockDim.x) {
+    const int c = o % C, t = o / C;
+    int acc_t = 0;
+    for (int j = 0; j < 4; ++j) {
+      const int cc = c + j - 1;
+      if (cc >= 0 && cc < C)
+        for (int ti = 0; ti < T; ++ti) acc_t += cnt[ti * C + cc] * (int)qt[(j * T + ti) * T + t];
+    }
+    tout[o] = acc_t;
+  }
+  // ---- c_out on the tensor cores
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+  int acc[2][2][4], acch[2][2][4];                                           // [m tile][n tile][fragment]
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int n = 0; n < 2; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { acc[m][n][e] = 0; acch[m][n][e] = 0; }
+  auto mma = [](int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  };
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t bf[2][2];
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        const int col = 16 * warp + 8 * n + g;
+        bf[n][0] = qc4[(j * C4 + ks * 8 + q) * SB + col];
+        bf[n][1] = qc4[(j * C4 + ks * 8 + q + 4) * SB + col];
+      }
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        // padded row of timestep t + j - 1 is t + j; rows beyond T + 1 are zero (ROWS = 36 >= 31 + 3 + 1)
+        const uint32_t *r0 = lo4 + (16 * m + g + j) * SA + ks * 8 + q, *r1 = r0 + 8 * SA;
+        const uint32_t a[4] = {r0[0], r1[0], r0[4], r1[4]};
+#pragma unroll
+        for (int n = 0; n < 2; ++n) mma(acc[m][n], a, bf[n][0], bf[n][1]);
+        if (any_hi) {
+          const uint32_t *h0 = hi4 + (16 * m + g + j) * SA + ks * 8 + q, *h1 = h0 + 8 * SA;
+          const uint32_t ah[4] = {h0[0], h1[0], h0[4], h1[4]};
+#pragma unroll
+          for (int n = 0; n < 2; ++n) mma(acch[m][n], ah, bf[n][0], bf[n][1]);
+        }
+      }
+    }
+  }
+  __syncthreads();                                                           // tout complete
+  const float st = *scale_t, scc = *scale_c;
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int n = 0; n < 2; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int t = 16 * m + g + 8 * (e >> 1), c = 16 * warp + 8 * n + 2 * q + (e & 1);
+        if (t >= T) continue;
+        const int acc_c = acc[m][n][e] + acch[m][n][e] * 256;
+        const float to = __fmul_rn((float)tout[t * C + c], st);
+        const float co = __fmul_rn((float)acc_c, scc);
+        const float pr = __fmul_rn(co, to);
+        const float a = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-pr)));
+        att[(int64_t)t * p.att_stride_t + (int64_t)b * p.att_stride_b + c] = a;
+      }
+}
+
 // 2x2 max-pool on uint8, 4 channels per thread (HBM-bound)
 __global__ void k_maxpool2(const snnqp_block_params p, const uint8_t *__restrict__ x,
                            uint8_t *__restrict__ y) {
@@ -609,8 +736,18 @@ int launch_tcja(const snnqp_block_params &p, const uint8_t *spikes, const int8_t
     k_tcja_counts<<<p.T * p.B, 256, 0, st>>>(p, spikes, counts);
     SNNQP_POST_LAUNCH("k_tcja_counts");
   }
-  if (p.Cin == 128 && p.T <= 32 && (int64_t)p.H * p.W <= 65535 && !(reinterpret_cast<uintptr_t>(counts) & 15) &&
-      !(reinterpret_cast<uintptr_t>(wq_c) & 15)) {
+  static const int tcja_impl = getenv("SNNQP_TCJA_IMPL") ? atoi(getenv("SNNQP_TCJA_IMPL")) : 2;   // 0 scalar, 1 dp4a, 2 mma.sync
+  const bool fast_ok = p.Cin == 128 && p.T <= 32 && (int64_t)p.H * p.W <= 65535 && !(reinterpret_cast<uintptr_t>(counts) & 15) &&
+                       !(reinterpret_cast<uintptr_t>(wq_c) & 15);
+  if (fast_ok && tcja_impl == 2) {
+    const size_t smem_m = (size_t)4 * 32 * 136 * 4 + (size_t)2 * 36 * 36 * 4 + (size_t)2 * p.T * 128 * sizeof(int32_t) +
+                          (size_t)4 * p.T * p.T + 16;
+    SNNQP_CUDA(cudaFuncSetAttribute(k_tcja_att_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m));
+    k_tcja_att_mma<<<p.B, 256, smem_m, st>>>(p, counts, wq_t, wq_c, scale_t, scale_c, att);
+    SNNQP_POST_LAUNCH("k_tcja_att_mma");
+    return SNNQP_OK;
+  }
+  if (fast_ok && tcja_impl == 1) {
     const size_t smem4 = (size_t)4 * 128 * 128 + (size_t)p.T * 128 * sizeof(int32_t) + (size_t)2 * (p.T + 3) * 32 * 4 +
                          (size_t)4 * p.T * p.T + 16;
     if ((int64_t)p.H * p.W <= 255) {
