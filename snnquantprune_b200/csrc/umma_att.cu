@@ -405,17 +405,37 @@ k_dense_umma(const __grid_constant__ CUtensorMap tmap_w, const DenseArgs a) {
       if (PLANES == 3) {
         // attention bytes of the tile rows, once per item: [pl][row][128]
         ptx::named_bar_sync(1, kExpWarps * 32);          // previous item's expander reads are done
-        for (int i = et; i < a.N * kC; i += kExpWarps * 32) {
-          const int r = i >> 7, ch = i & 127;
-          const int row = row0 + r;
-          uint32_t fx = 0;
-          if (row < rows_total) {
-            const int b = row / a.T, t = row % a.T;
-            fx = ptx::att_fix24(a.att[(int64_t)t * a.att_stride_t + (int64_t)b * a.att_stride_b + ch]);
+        // four channels per thread and iteration (one 16-byte load, three word stores), eight independent loads in
+        // flight: one scalar load per iteration left ~160 exposed global-memory latencies per item and made this
+        // loop, not the MMAs, the kernel's critical path
+        constexpr int kU = 8;
+        for (int i0 = et; i0 < a.N * (kC / 4); i0 += kU * kExpWarps * 32) {
+          float4 v[kU];
+#pragma unroll
+          for (int u = 0; u < kU; ++u) {
+            const int i4 = i0 + u * kExpWarps * 32;
+            const int row = row0 + (i4 >> 5);
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i4 < a.N * (kC / 4) && row < rows_total) {
+              const int b = row / a.T, t = row % a.T;
+              v[u] = __ldg(reinterpret_cast<const float4 *>(a.att + (int64_t)t * a.att_stride_t + (int64_t)b * a.att_stride_b) +
+                           (i4 & 31));
+            }
           }
-          att_smem[0 * kBPlane + i] = (uint8_t)(fx >> 16);
-          att_smem[1 * kBPlane + i] = (uint8_t)(fx >> 8);
-          att_smem[2 * kBPlane + i] = (uint8_t)fx;
+#pragma unroll
+          for (int u = 0; u < kU; ++u) {
+            const int i4 = i0 + u * kExpWarps * 32;
+            if (i4 >= a.N * (kC / 4)) break;
+            const uint32_t f0 = ptx::att_fix24(v[u].x), f1 = ptx::att_fix24(v[u].y), f2 = ptx::att_fix24(v[u].z),
+                           f3 = ptx::att_fix24(v[u].w);
+            // byte plane pl of channels (4k .. 4k+3): byte (2 - pl) of each fixed-point word
+            const uint32_t lo01 = __byte_perm(f0, f1, 0x5140), lo23 = __byte_perm(f2, f3, 0x5140);   // (f0.b0 f1.b0 f0.b1 f1.b1)
+            const uint32_t hi01 = __byte_perm(f0, f1, 0x7362), hi23 = __byte_perm(f2, f3, 0x7362);   // (f0.b2 f1.b2 f0.b3 f1.b3)
+            uint32_t *dst = reinterpret_cast<uint32_t *>(att_smem) + i4;
+            dst[0 * (kBPlane / 4)] = __byte_perm(hi01, hi23, 0x5410);      // b2 of the four channels
+            dst[1 * (kBPlane / 4)] = __byte_perm(lo01, lo23, 0x7632);      // b1
+            dst[2 * (kBPlane / 4)] = __byte_perm(lo01, lo23, 0x5410);      // b0
+          }
         }
         ptx::named_bar_sync(1, kExpWarps * 32);
       }
@@ -607,6 +627,8 @@ bool umma_dense_supported(const snnqp_block_params &p, const float *att, int k_p
   if (!dense_tile(p.T, &NB, &N)) return false;
   if (p.x_stride_t != p.Cin || p.x_stride_b != (int64_t)p.T * p.Cin) return false;   // rows (b,t) contiguous
   if (att && p.att_mod != kC) return false;
+  // the attention rows are read as float4
+  if (att && ((reinterpret_cast<uintptr_t>(att) & 15) || (p.att_stride_t & 3) || (p.att_stride_b & 3))) return false;
   return true;
 }
 
