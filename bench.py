@@ -124,8 +124,14 @@ def run_reference(args):
   torch.set_num_threads(threads)
   v = synthetic.make_variables(bits=args.bits, prune_percentage=args.prune, T=T, H=H, seed=1)
   fr = synthetic.make_frames(sample_B, T, H, H, seed=0)
-  for _ in range(args.warmup):
+  t1 = None
+  for _ in range(max(1, args.warmup)):
+    t0 = time.perf_counter()
     ref_snn.cextnet_forward(v, fr[:1], args.bits)
+    t1 = time.perf_counter() - t0                     # seconds per sample, last warm-up pass
+  # bounded sample: the K timed steps together take about two and a half minutes at most, whatever K is
+  sample_B = max(1, min(sample_B, int(150.0 / (max(1, args.steps) * max(t1, 1e-3)))))
+  fr = fr[:sample_B]
   t0 = time.perf_counter()
   for _ in range(args.steps):
     ref_snn.cextnet_forward(v, fr, args.bits)
@@ -137,7 +143,7 @@ def run_reference(args):
       "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
       "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-      "config": workload_config(args, sample_B, 1),
+      "config": dict(workload_config(args, args.batch, max(1, args.gpus)), reference_samples_per_step=sample_B),
       "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
       "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
       "gpu_launches": 0,
