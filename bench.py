@@ -6,10 +6,11 @@
 
 A "step" is one pass of the hot path (frames on device -> logits on device) over
 one batch of synthetic event frames.  Workload at N GPUs = BASELINE.json
-configs[4] sharded by batch: 8-bit weights, 50 % global magnitude pruning, T=20,
-128x128x2 frames, 512 samples per GPU (4096 at N=8), weak scaling, no collective
-on the hot path (one NCCL all-reduce of the accuracy counters after the timed
-region).  Prints ONE JSON line on rank 0.
+configs[4]: a batch of 4096 samples sharded over the N GPUs (4096 / N each:
+strong scaling; --batch gives a fixed per-GPU batch instead), 8-bit weights, 50 %
+global magnitude pruning, T=20, 128x128x2 frames, no collective on the hot path
+(one NCCL all-reduce of the accuracy counters after the timed region).  Prints
+ONE JSON line on rank 0.
 
 The reference itself (JAX/Flax) cannot be installed or imported in this image
 (no jax / flax / ml_collections wheels, no network), so
@@ -142,8 +143,10 @@ def run_reference(args):
   line = {
       "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
       "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-      "config": dict(workload_config(args, args.batch, max(1, args.gpus)), reference_samples_per_step=sample_B),
+      "higher_is_better": True, "scaling": "strong" if args.batch is None else "weak", "vs_baseline": None,
+      "dtype": "f32", "data": "synthetic",
+      "config": dict(workload_config(args, args.batch if args.batch is not None else args.global_batch // max(1, args.gpus),
+                                     max(1, args.gpus)), reference_samples_per_step=sample_B),
       "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
       "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
       "gpu_launches": 0,
@@ -180,7 +183,10 @@ def run_ours(args):
     raise SystemExit("bench.py needs an sm_100 GPU: " + lib.snnqp_last_error().decode())
   impl = {"auto": _lib.IMPL_AUTO, "simt": _lib.IMPL_SIMT, "tcgen05": _lib.IMPL_TCGEN05}[args.kernels]
 
-  B, T, H = args.batch, args.T, args.H
+  if args.batch is None and args.global_batch % ws:
+    raise SystemExit(f"--global-batch {args.global_batch} must be divisible by the number of GPUs ({ws})")
+  B = args.batch if args.batch is not None else args.global_batch // ws
+  T, H = args.T, args.H
   v = synthetic.make_variables(bits=args.bits, prune_percentage=args.prune, T=T, H=H, seed=1)
   packed = pack_cextnet(v, args.bits, T, H, device=dev)
   eng = CextNetEngine(packed, impl=impl, chunk=args.chunk, device=dev)
@@ -257,7 +263,8 @@ def run_ours(args):
     net_tops = value * GOP_PER_SAMPLE_T20 / 1e3 / ws          # dense-equivalent int8 TOP/s per GPU
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+        "scaling": "strong" if args.batch is None else "weak", "vs_baseline": None,
         "dtype": "int8", "data": "synthetic",
         "config": dict(workload_config(args, B, ws),
                        arithmetic="int8 weights x u8 spikes/counts -> int32 accumulate (tcgen05 kind::i8; conv1 as exact "
@@ -349,7 +356,9 @@ def main():
   ap.add_argument("--warmup", type=int, default=3)
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
   ap.add_argument("--kernels", default="auto", choices=["auto", "simt", "tcgen05"])
-  ap.add_argument("--batch", type=int, default=512, help="samples per GPU per step")
+  ap.add_argument("--global-batch", type=int, default=4096,
+                  help="samples per step over all GPUs (BASELINE.json configs[4]: batch 4096 sharded over 1/2/4/8 GPUs)")
+  ap.add_argument("--batch", type=int, default=None, help="samples per GPU per step (overrides --global-batch: weak scaling)")
   ap.add_argument("--chunk", type=int, default=256, help="samples per head launch (large: exact CTA waves; L2 residency measured irrelevant)")
   ap.add_argument("--bits", type=int, default=8)
   ap.add_argument("--prune", type=float, default=0.5)

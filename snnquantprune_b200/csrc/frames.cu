@@ -145,13 +145,18 @@ extern "C" int snnqp_slice_nonzeros(const uint8_t *x, int n_slices, int64_t slic
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   if (!x || !counts) return invalid("snnqp_slice_nonzeros: null pointer");
   if (n_slices <= 0 || slice_bytes <= 0) return invalid("snnqp_slice_nonzeros: n_slices and slice_bytes must be > 0");
-  if (n_slices > 65535) return unsupported("snnqp_slice_nonzeros: more than 65535 slices");
   const int vec16 = !((reinterpret_cast<uintptr_t>(x) & 15) || (stride_slice & 15));
   SNNQP_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * n_slices, st));
   int bx = (int)((slice_bytes / 16 + 255) / 256);
   const int cap = (8 * sm_count() + n_slices - 1) / n_slices;          // ~8 CTAs per SM over the whole grid
   bx = bx < 1 ? 1 : (bx > cap ? (cap < 1 ? 1 : cap) : bx);
-  k_slice_nonzeros<<<dim3(bx, n_slices), 256, 0, st>>>(x, slice_bytes, stride_slice, vec16, counts);
-  SNNQP_POST_LAUNCH("k_slice_nonzeros");
+  for (int s0 = 0; s0 < n_slices; s0 += 65535) {                         // gridDim.y limit
+    const int ns = n_slices - s0 < 65535 ? n_slices - s0 : 65535;
+    k_slice_nonzeros<<<dim3(bx, ns), 256, 0, st>>>(x + (int64_t)s0 * stride_slice, slice_bytes, stride_slice, vec16,
+                                                    counts + s0);
+    count_launch();
+  }
+  if (cudaError_t e = cudaGetLastError()) return cuda_fail(e, "k_slice_nonzeros");
   return SNNQP_OK;
 }
+

@@ -98,7 +98,7 @@ def test_events_feed_the_hot_path(cuda_lib):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape", [(4, 3, 16, 16, 128), (2, 5, 7, 16), (20, 2, 64, 64, 128), (3, 4, 110), (2, 2, 5)])
+@pytest.mark.parametrize("shape", [(4, 3, 16, 16, 128), (2, 5, 7, 16), (20, 2, 64, 64, 128), (3, 4, 110), (2, 2, 5), (70001, 1, 48)])
 def test_density_stats_bit_exact(cuda_lib, shape):
   from snnquantprune_b200 import input_pipeline as ip
   rng = np.random.default_rng(len(shape))
