@@ -73,4 +73,59 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(SnnqpSpikingDense, SpikingDenseImpl,
                                   .Attr<float>("tau")
                                   .Attr<float>("v_threshold")
                                   .Attr<float>("v_reset"));
+
+// TCJA (models.py:41-95) from the spike counts a conv block accumulated; att: (B,T,C) fp32
+static ffi::Error TcjaImpl(cudaStream_t stream, ffi::Buffer<ffi::S32> counts, ffi::Buffer<ffi::S8> wq_t,
+                           ffi::Buffer<ffi::S8> wq_c, ffi::Buffer<ffi::F32> scale_t, ffi::Buffer<ffi::F32> scale_c,
+                           ffi::ResultBuffer<ffi::F32> att, int32_t spatial) {
+  auto d = counts.dimensions();                 // (B, T, C)
+  snnqp_block_params p{};
+  p.B = (int32_t)d[0]; p.T = (int32_t)d[1]; p.Cin = p.Cout = (int32_t)d[2]; p.H = p.W = spatial;
+  p.att_stride_t = p.Cin; p.att_stride_b = (int64_t)p.T * p.Cin; p.att_mod = p.Cin;
+  return Status(snnqp_tcja_fwd(&p, nullptr, wq_t.typed_data(), wq_c.typed_data(), scale_t.typed_data(),
+                               scale_c.typed_data(), counts.typed_data(), att->typed_data(), stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(SnnqpTcja, TcjaImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::S8>>()
+                                  .Arg<ffi::Buffer<ffi::S8>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .Attr<int32_t>("spatial"));
+
+// vote (models.py:253-255): spikes (B,T,N) uint8 -> logits (B, N / group) fp32
+static ffi::Error VoteImpl(cudaStream_t stream, ffi::Buffer<ffi::U8> spikes, ffi::ResultBuffer<ffi::F32> logits,
+                           int32_t group) {
+  auto d = spikes.dimensions();
+  return Status(snnqp_vote_fwd(spikes.typed_data(), (int)d[1], (int)d[0], (int)d[2], group, d[2], d[1] * d[2],
+                               logits->typed_data(), stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(SnnqpVote, VoteImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::U8>>()
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .Attr<int32_t>("group"));
+
+// event -> frame integration (examples/input_pipeline.py:142-219): addrs (N,3) int32, offsets (B+1) int64
+static ffi::Error EventsToFramesImpl(cudaStream_t stream, ffi::Buffer<ffi::S32> addrs, ffi::Buffer<ffi::S64> offsets,
+                                     ffi::ResultBuffer<ffi::U8> frames, int32_t sensor_wh, int32_t resolution_scale,
+                                     int64_t max_events_per_sample) {
+  auto f = frames->dimensions();                // (B, T, wh, wh, 2)
+  return Status(snnqp_events_to_frames(addrs.typed_data(), offsets.typed_data(), (int)f[0], (int)f[1], sensor_wh,
+                                       resolution_scale, max_events_per_sample, frames->typed_data(), 0, nullptr,
+                                       stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(SnnqpEventsToFrames, EventsToFramesImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::S64>>()
+                                  .Ret<ffi::Buffer<ffi::U8>>()
+                                  .Attr<int32_t>("sensor_wh")
+                                  .Attr<int32_t>("resolution_scale")
+                                  .Attr<int64_t>("max_events_per_sample"));
 #endif  // SNNQP_HAVE_XLA_FFI
