@@ -189,3 +189,20 @@ def test_evaluate_rejects_indivisible_batch_like_reference():
       evaluate(_toy_forward, _toy_batches(1, 6), metrics_fn=_torch_metrics)
   finally:
     del os.environ["WORLD_SIZE"]
+
+
+def test_host_chunk_schedule_covers_batch_and_respects_cap():
+  """forward_host's chunk schedule: contiguous cover of [0, B), every chunk <= engine.chunk, small first chunk,
+  non-decreasing until the cap (the last chunk takes the remainder)."""
+  from snnquantprune_b200.engine import CextNetEngine
+  eng = object.__new__(CextNetEngine)
+  for cap in (1, 2, 16, 128, 256):
+    eng.chunk = cap
+    for B in (1, 5, 16, 17, 512, 4096, 4099):
+      sched = eng.host_chunks(B)
+      assert sched[0][0] == 0 and sum(n for _, n in sched) == B
+      assert all(b1 == b0 + n0 for (b0, n0), (b1, _) in zip(sched, sched[1:]))
+      assert all(0 < n <= cap for _, n in sched)
+      assert sched[0][1] == min(16, cap, B)
+      body = [n for _, n in sched[:-1]]
+      assert body == sorted(body)
