@@ -225,7 +225,7 @@ class CextNetEngine:
       m = min(int(n), self.chunk, B - b0)
       out.append((b0, m))
       b0 += m
-      n = max(n * growth, n + 1)
+      n = min(max(n * growth, n + 1), float(self.chunk))
     return out
 
   def forward_host(self, host_frames: torch.Tensor, out_host: Optional[torch.Tensor] = None) -> torch.Tensor:
