@@ -359,13 +359,13 @@ def main():
   ap.add_argument("--global-batch", type=int, default=4096,
                   help="samples per step over all GPUs (BASELINE.json configs[4]: batch 4096 sharded over 1/2/4/8 GPUs)")
   ap.add_argument("--batch", type=int, default=None, help="samples per GPU per step (overrides --global-batch: weak scaling)")
-  ap.add_argument("--chunk", type=int, default=256, help="samples per head launch (large: exact CTA waves; L2 residency measured irrelevant)")
+  ap.add_argument("--chunk", type=int, default=296, help="samples per head launch: a multiple of 37 makes the strip / item counts of conv1-3 exact multiples of the 148 persistent CTAs (296 -> 256 / 64 / 16 waves)")
   ap.add_argument("--bits", type=int, default=8)
   ap.add_argument("--prune", type=float, default=0.5)
   ap.add_argument("--T", type=int, default=20)
   ap.add_argument("--H", type=int, default=128)
   ap.add_argument("--e2e-steps", type=int, default=5)
-  ap.add_argument("--e2e-chunk", type=int, default=256, help="largest H2D / head chunk of the end-to-end path (chunks grow from 16)")
+  ap.add_argument("--e2e-chunk", type=int, default=296, help="largest H2D / head chunk of the end-to-end path (chunks grow from 16)")
   ap.add_argument("--cpu-batch", type=int, default=8)
   ap.add_argument("--ref-batch", type=int, default=8)
   ap.add_argument("--no-cpu-baseline", action="store_true")

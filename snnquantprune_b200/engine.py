@@ -31,7 +31,7 @@ from .pack import PackedCextNet
 class CextNetEngine:
   def __init__(self, packed: PackedCextNet, impl: int = _lib.IMPL_AUTO,
                tau: float = 2.0, v_threshold: float = 1.0, v_reset: float = 0.0,
-               chunk: int = 256, device="cuda"):
+               chunk: int = 296, device="cuda"):
     self.pk = packed
     self.impl = impl
     self.tau, self.v_th, self.v_reset = tau, v_threshold, v_reset

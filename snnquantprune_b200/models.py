@@ -34,7 +34,7 @@ class CextNet:
   config: ModelConfig = field(default_factory=ModelConfig)
   load_model_fn: Optional[Callable] = None
   impl: int = _lib.IMPL_AUTO
-  chunk: int = 256
+  chunk: int = 296
 
   def __post_init__(self):
     self._engine: Optional[CextNetEngine] = None
