@@ -48,9 +48,13 @@ __device__ __forceinline__ uint32_t nz_mask4(uint32_t w) { return __vcmpne4(w, 0
 // conv-att: W = 8, strips of 8 rows, P = 10, N = 80
 // =====================================================================================
 namespace ca {
-constexpr int W = 8, TH = 8, P = 10, N = 80;
-constexpr int kPlaneBytes = 13312;                 // 104 rows x 128 B (>= 2P+2+N rows), 1024-aligned
-constexpr int kStageBytes = 3 * kPlaneBytes;
+// The three byte planes are INTERLEAVED at position granularity: operand row 3*pos + plane, accumulator column
+// 3*pos + plane.  A flat shift by s positions is then a shift by 3*s rows, and ONE MMA of N = 240 covers the 80 flat
+// positions of all three planes: 36 MMAs per step at the full-width rate instead of 108 of N = 80 (N = 80 runs at
+// 75 % of the N = 240 rate: profiles/README.md).
+constexpr int W = 8, TH = 8, P = 10, N = 80, NI = 3 * N;
+constexpr int kPlaneBytes = 13312;                 // 104 rows x 128 B (>= 2P+2+N rows) per plane
+constexpr int kStageBytes = 3 * kPlaneBytes;       // 312 interleaved rows, 1024-aligned
 constexpr int kWBytes = 9 * kC * kC, kTapBytes = kC * kC;
 constexpr int kEpiWarps = 8, kExpWarps = 4;
 constexpr int kThreads = (kEpiWarps + 1 + kExpWarps) * 32;   // 416
@@ -120,7 +124,7 @@ k_conv_att_umma(const __grid_constant__ CUtensorMap tmap_w, const ConvAttArgs a)
         for (int i = 0; i < 36; ++i) nz_mask |= (uint64_t)(a.slab_nz[i] != 0) << i;
         if (nz_mask == 0) nz_mask = 1;
       }
-      const uint32_t idesc = ptx::make_idesc_i8(128, N, true, false);
+      const uint32_t idesc = ptx::make_idesc_i8(128, NI, true, false);
       const uint32_t w_addr = ptx::smem_u32(w_smem);
       const uint64_t desc_hi = ptx::make_desc_sw128(0, 0);
       const bool dense_path = (nz_mask & 0xFFFFFFFFFull) == 0xFFFFFFFFFull;
@@ -135,27 +139,24 @@ k_conv_att_umma(const __grid_constant__ CUtensorMap tmap_w, const ConvAttArgs a)
           const uint32_t x_addr = ptx::smem_u32(stage_smem + s * kStageBytes);
           // descriptors: constant high half + 14-bit start address in 16-byte units (never carries out)
           const uint64_t ad0 = desc_hi + (w_addr >> 4);
-#pragma unroll 1
-          for (int pl = 0; pl < 3; ++pl) {
-            const uint32_t d_tmem = tmem_base + s * kAccStride + pl * N;
-            const uint64_t bd0 = desc_hi + ((x_addr + pl * kPlaneBytes) >> 4);
-            if (dense_path) {
+          const uint32_t d_tmem = tmem_base + s * kAccStride;
+          const uint64_t bd0 = desc_hi + (x_addr >> 4);
+          if (dense_path) {
 #pragma unroll
-              for (int tap = 0; tap < 9; ++tap)
+            for (int tap = 0; tap < 9; ++tap)
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  ptx::mma_i8(d_tmem, ad0 + (tap * kTapBytes + k * 32) / 16,
-                              bd0 + (((tap / 3) * P + (tap % 3)) * 128 + k * 32) / 16, idesc, (tap | k) != 0);
-            } else {
-              uint32_t accumulate = 0;
-#pragma unroll 1
-              for (int sl = 0; sl < 36; ++sl) {
-                if (!((nz_mask >> sl) & 1)) continue;      // block-sparse skip of an all-zero K-slab
-                const int tap = sl >> 2, k = sl & 3;
+              for (int k = 0; k < 4; ++k)
                 ptx::mma_i8(d_tmem, ad0 + (tap * kTapBytes + k * 32) / 16,
-                            bd0 + (((tap / 3) * P + (tap % 3)) * 128 + k * 32) / 16, idesc, accumulate);
-                accumulate = 1;
-              }
+                            bd0 + (3 * ((tap / 3) * P + (tap % 3)) * 128 + k * 32) / 16, idesc, (tap | k) != 0);
+          } else {
+            uint32_t accumulate = 0;
+#pragma unroll 1
+            for (int sl = 0; sl < 36; ++sl) {
+              if (!((nz_mask >> sl) & 1)) continue;      // block-sparse skip of an all-zero K-slab
+              const int tap = sl >> 2, k = sl & 3;
+              ptx::mma_i8(d_tmem, ad0 + (tap * kTapBytes + k * 32) / 16,
+                          bd0 + (3 * ((tap / 3) * P + (tap % 3)) * 128 + k * 32) / 16, idesc, accumulate);
+              accumulate = 1;
             }
           }
           ptx::mma_commit(in_empty + s);
@@ -189,14 +190,14 @@ k_conv_att_umma(const __grid_constant__ CUtensorMap tmap_w, const ConvAttArgs a)
           if (ih >= 0 && ih < a.H && iw >= 0 && iw < W)
             sv = __ldg(reinterpret_cast<const int4 *>(xb + ((int64_t)ih * W + iw) * kC + c16 * 16));
           const uint32_t m0 = nz_mask4(sv.x), m1 = nz_mask4(sv.y), m2 = nz_mask4(sv.z), m3 = nz_mask4(sv.w);
-          const uint32_t off = (uint32_t)(pix * 128 + ((c16 ^ (pix & 7)) << 4));
 #pragma unroll
           for (int pl = 0; pl < 3; ++pl) {
             const int4 av = *reinterpret_cast<const int4 *>(ab + pl * kC + c16 * 16);
             int4 o;
             o.x = (int)(m0 & (uint32_t)av.x); o.y = (int)(m1 & (uint32_t)av.y);
             o.z = (int)(m2 & (uint32_t)av.z); o.w = (int)(m3 & (uint32_t)av.w);
-            *reinterpret_cast<int4 *>(dst + pl * kPlaneBytes + off) = o;
+            const int row = 3 * pix + pl;                  // interleaved operand row (swizzle on absolute row bits)
+            *reinterpret_cast<int4 *>(dst + row * 128 + ((c16 ^ (row & 7)) << 4)) = o;
           }
         }
         ptx::fence_proxy_async();
@@ -224,14 +225,18 @@ k_conv_att_umma(const __grid_constant__ CUtensorMap tmap_w, const ConvAttArgs a)
         const uint32_t s = step & 1, ph = (step >> 1) & 1;
         ptx::mbar_wait(acc_full + s, ph);
         ptx::tc_fence_after();
-        uint32_t acc[3][4][8];
+        uint32_t acc[4][24];                               // [row][3 * column + plane]
 #pragma unroll
-        for (int pl = 0; pl < 3; ++pl)
+        for (int r = 0; r < 4; ++r) {
+          const uint32_t taddr = lane_addr + s * kAccStride + 3 * (r0 + r) * P;
+          uint32_t lo[16], hi[8];
+          SNNQP_TMEM_LD_X16(taddr, lo);
+          SNNQP_TMEM_LD_X8(taddr + 16, hi);
 #pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            const uint32_t taddr = lane_addr + s * kAccStride + pl * N + (r0 + r) * P;
-            SNNQP_TMEM_LD_X8(taddr, acc[pl][r]);
-          }
+          for (int i = 0; i < 16; ++i) acc[r][i] = lo[i];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[r][16 + i] = hi[i];
+        }
         ptx::tc_wait_ld();
         ptx::tc_fence_before();
         __syncwarp();
@@ -244,7 +249,7 @@ k_conv_att_umma(const __grid_constant__ CUtensorMap tmap_w, const ConvAttArgs a)
           m[r] = 0;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float accf = ptx::att_combine((int32_t)acc[0][r][j], (int32_t)acc[1][r][j], (int32_t)acc[2][r][j]);
+            const float accf = ptx::att_combine((int32_t)acc[r][3 * j], (int32_t)acc[r][3 * j + 1], (int32_t)acc[r][3 * j + 2]);
             const float v = __fmaf_rn(accf, sc, bi);
             bool sp;
             if constexpr (TAU2) {
