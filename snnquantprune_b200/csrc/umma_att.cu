@@ -175,21 +175,33 @@ k_conv_att_umma(const __grid_constant__ CUtensorMap tmap_w, const ConvAttArgs a)
         // attention bytes of this (t, b): thread = channel
         uint8_t *ab = att_smem + s * 3 * kC;
         const uint32_t fx = ptx::att_fix24(a.att[(int64_t)t * a.att_stride_t + (int64_t)b * a.att_stride_b + et]);
+        // every global load of the step (the attention word above and the thread's 7 spike chunks) is issued BEFORE
+        // the wait for the stage: the loads do not depend on it, and their latency then hides behind the MMAs that
+        // still read the stage (the ncu source view had the expanders 69 % of their time on these loads)
+        const uint8_t *xb = a.x + (int64_t)t * a.x_stride_t + (int64_t)b * a.x_stride_b;
+        constexpr int kChunks = (TH + 2) * P * 8, kIt = (kChunks + kExpWarps * 32 - 1) / (kExpWarps * 32);
+        int4 sv[kIt];
+#pragma unroll
+        for (int it = 0; it < kIt; ++it) {
+          const int ch = et + it * kExpWarps * 32;
+          const int pix = ch >> 3, c16 = ch & 7;
+          const int ih = h0 - 1 + pix / P, iw = pix % P - 1;
+          sv[it] = make_int4(0, 0, 0, 0);
+          if (ch < kChunks && ih >= 0 && ih < a.H && iw >= 0 && iw < W)
+            sv[it] = __ldg(reinterpret_cast<const int4 *>(xb + ((int64_t)ih * W + iw) * kC + c16 * 16));
+        }
         ptx::mbar_wait(in_empty + s, ph ^ 1);        // stage (and its att bytes) no longer read by the MMAs
         ab[0 * kC + et] = (uint8_t)(fx >> 16);
         ab[1 * kC + et] = (uint8_t)(fx >> 8);
         ab[2 * kC + et] = (uint8_t)fx;
         ptx::named_bar_sync(1, kExpWarps * 32);
-        const uint8_t *xb = a.x + (int64_t)t * a.x_stride_t + (int64_t)b * a.x_stride_b;
         uint8_t *dst = stage_smem + s * kStageBytes;
-        for (int ch = et; ch < (TH + 2) * P * 8; ch += kExpWarps * 32) {
+#pragma unroll
+        for (int it = 0; it < kIt; ++it) {
+          const int ch = et + it * kExpWarps * 32;
+          if (ch >= kChunks) break;
           const int pix = ch >> 3, c16 = ch & 7;
-          const int hh = pix / P, ww = pix % P;
-          const int ih = h0 - 1 + hh, iw = ww - 1;
-          int4 sv = make_int4(0, 0, 0, 0);
-          if (ih >= 0 && ih < a.H && iw >= 0 && iw < W)
-            sv = __ldg(reinterpret_cast<const int4 *>(xb + ((int64_t)ih * W + iw) * kC + c16 * 16));
-          const uint32_t m0 = nz_mask4(sv.x), m1 = nz_mask4(sv.y), m2 = nz_mask4(sv.z), m3 = nz_mask4(sv.w);
+          const uint32_t m0 = nz_mask4(sv[it].x), m1 = nz_mask4(sv[it].y), m2 = nz_mask4(sv[it].z), m3 = nz_mask4(sv[it].w);
 #pragma unroll
           for (int pl = 0; pl < 3; ++pl) {
             const int4 av = *reinterpret_cast<const int4 *>(ab + pl * kC + c16 * 16);
