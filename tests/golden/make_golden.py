@@ -17,7 +17,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
-from oracle import ref_int, ref_net, ref_quant, ref_snn  # noqa: E402
+from oracle import ref_events, ref_int, ref_net, ref_quant, ref_snn  # noqa: E402
 from snnquantprune_b200 import synthetic  # noqa: E402
 
 
@@ -86,9 +86,36 @@ def network_fixture(bits, p, T, H, B, seed_w, seed_x):
   return fx
 
 
+def events_fixture():
+  """Ragged batch of event lists (one empty, one shorter than T, one with a hot pixel that saturates uint8 and
+  events beyond the row / frame) -> frames of the oracle's preprocess_data_number, for two resolution scales,
+  plus the sowed densities of the uint8 frames."""
+  rng = np.random.default_rng(21)
+  wh, T = 32, 6
+  sizes = [4000, 0, 4, 2500]
+  samples = []
+  for n in sizes:
+    a = np.stack([rng.integers(0, wh, n), rng.integers(0, wh, n), rng.integers(0, 3, n)], 1).astype(np.int32)
+    samples.append(a)
+  samples[0][:600, :2] = [7, 3]                       # hot pixel: > 255 events in one frame
+  samples[3][::50, 0] = wh + 1                        # beyond the row: lands in the next row (flat position)
+  samples[3][-3:, 1] = wh + 2                         # beyond the frame: dropped
+  fx = {"addrs": np.concatenate(samples, 0), "offsets": np.cumsum([0] + sizes).astype(np.int64),
+        "wh": np.array(wh), "T": np.array(T)}
+  for rs in (1, 2):
+    f32 = ref_events.batch_to_frames(samples, T, wh, rs)
+    f8, nsat = ref_events.batch_to_frames(samples, T, wh, rs, saturate_u8=True)
+    fx[f"frames_i32_rs{rs}"] = f32
+    fx[f"n_saturated_rs{rs}"] = np.array(nsat)
+    d = ref_events.sow_densities(np.swapaxes(f8, 0, 1))
+    fx[f"density_counts_rs{rs}"] = d["counts"]
+  return fx
+
+
 if __name__ == "__main__":
   with open(os.path.join(HERE, "duq_vectors.json"), "w") as f:
     json.dump(duq_vectors(), f)
+  np.savez_compressed(os.path.join(HERE, "events_T6_wh32.npz"), **events_fixture())
   np.savez_compressed(os.path.join(HERE, "cextnet_T4_H32_b8_p50.npz"),
                       **network_fixture(8, 0.5, 4, 32, 2, 1, 0))
   np.savez_compressed(os.path.join(HERE, "cextnet_T3_H32_b4_p80.npz"),

@@ -125,3 +125,46 @@ def test_engine_densities_match_oracle(cuda_lib):
     w = ref_events.sow_densities(np.swapaxes(x, 0, 1))             # (T, B, ...)
     assert abs(d[key]["min"] - w["min"]) < 1e-12 and abs(d[key]["mean"] - w["mean"]) < 1e-12, key
   assert 0.0 < d["conv_1_inpt"]["mean"] < 1.0
+
+
+# ---- committed golden fixture (tests/golden/make_golden.py: events_fixture) ---------------------------------------
+import os
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "events_T6_wh32.npz")
+
+
+def _gold_samples(z):
+  off = z["offsets"]
+  return [z["addrs"][off[i]:off[i + 1]] for i in range(len(off) - 1)]
+
+
+def test_oracle_matches_events_golden_fixture():
+  z = np.load(GOLD)
+  wh, T = int(z["wh"]), int(z["T"])
+  samples = _gold_samples(z)
+  for rs in (1, 2):
+    assert np.array_equal(ref_events.batch_to_frames(samples, T, wh, rs), z[f"frames_i32_rs{rs}"])
+    f8, nsat = ref_events.batch_to_frames(samples, T, wh, rs, saturate_u8=True)
+    assert nsat == int(z[f"n_saturated_rs{rs}"]) and nsat > 0
+    assert np.array_equal(ref_events.sow_densities(np.swapaxes(f8, 0, 1))["counts"], z[f"density_counts_rs{rs}"])
+  # structure of the fixture: the empty sample gives empty frames, the 4-event sample puts everything in the last frame
+  f = z["frames_i32_rs1"]
+  assert f[1].sum() == 0 and f[2, :-1].sum() == 0 and f[2, -1].sum() == 4
+
+
+@pytest.mark.gpu
+def test_events_and_density_kernels_match_golden_fixture(cuda_lib):
+  from snnquantprune_b200 import input_pipeline as ip
+  z = np.load(GOLD)
+  wh, T = int(z["wh"]), int(z["T"])
+  samples = _gold_samples(z)
+  addrs, off = ip.concat_events(samples)
+  assert np.array_equal(addrs.numpy(), z["addrs"]) and np.array_equal(off.numpy(), z["offsets"])
+  for rs in (1, 2):
+    for bound in (0, 4000):
+      f32, _ = ip.events_to_frames(addrs.cuda(), off.cuda(), T, wh, rs, exact_int32=True, max_events_per_sample=bound)
+      assert np.array_equal(f32.cpu().numpy(), z[f"frames_i32_rs{rs}"])
+      f8, sat = ip.events_to_frames(addrs.cuda(), off.cuda(), T, wh, rs, max_events_per_sample=bound)
+      assert np.array_equal(f8.cpu().numpy(), np.minimum(z[f"frames_i32_rs{rs}"], 255).astype(np.uint8))
+      assert int(sat.item()) == int(z[f"n_saturated_rs{rs}"])
+    d = ip.density_stats(f8, f8.shape[0] * T)
+    assert np.array_equal(d["counts"].cpu().numpy().reshape(f8.shape[0], T).T, z[f"density_counts_rs{rs}"])
