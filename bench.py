@@ -141,7 +141,7 @@ def run_reference(args):
   sample = (f"{sample_B} samples/step of the same workload (bits={args.bits}, prune={args.prune}, T={T}, "
             f"{H}x{H}x2), oracle fp32 restatement (torch-CPU conv2d/matmul), {threads} threads")
   line = {
-      "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+      "impl": "reference", "metric": METRIC.replace("T=20", f"T={args.T}"), "value": val, "unit": UNIT, "n_gpus": args.gpus,
       "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
       "higher_is_better": True, "scaling": "strong" if args.batch is None else "weak", "vs_baseline": None,
       "dtype": "f32", "data": "synthetic",
@@ -262,7 +262,7 @@ def run_ours(args):
                        f"of the reference graph (torch-CPU contractions); the JAX reference cannot run in this image"}
     net_tops = value * GOP_PER_SAMPLE_T20 / 1e3 / ws          # dense-equivalent int8 TOP/s per GPU
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC.replace("T=20", f"T={args.T}"), "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True,
         "scaling": "strong" if args.batch is None else "weak", "vs_baseline": None,
         "dtype": "int8", "data": "synthetic",
