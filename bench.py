@@ -59,8 +59,8 @@ class ClockSampler:
     self.stop_flag = False
 
   def _run(self):
-    import pynvml as N
     try:
+      import pynvml as N
       N.nvmlInit()
       h = N.nvmlDeviceGetHandleByIndex(self.idx)
       mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
