@@ -47,6 +47,53 @@ _IN_M2 = (0.1725, 0.27, 0.36, 0.32, 0.06)
 _CONV_NAMES = ("QuantConv_0", "QuantConv_1", "QuantConv_2", "QuantConv_3", "QuantConv_6")
 
 
+class StableRNG:
+  """Counter-based generator built from integer arithmetic only (splitmix64 over
+  a running counter), so its streams are identical on every numpy / libm:
+  fixtures keyed on it can FAIL (not skip) on a digest mismatch.  `uniform`
+  is exact 53-bit; `standard_normal` is Irwin-Hall(4) of 16-bit lanes (unit
+  variance, support +-3.46 sigma) -- enough for synthetic weights; `poisson15`
+  inverts a fixed 4-entry CDF table of Poisson(0.15) (counts >= 4, P = 2e-5,
+  are reported as 4)."""
+
+  def __init__(self, seed: int):
+    self.ctr = np.uint64((int(seed) * 0x9E3779B97F4A7C15 + 0x632BE59BD9B4E019) & 0xFFFFFFFFFFFFFFFF)
+
+  def _u64(self, n: int) -> np.ndarray:
+    with np.errstate(over="ignore"):
+      z = self.ctr + (np.arange(1, n + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15))
+      self.ctr = z[-1] if n else self.ctr
+      z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+      z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+      return z ^ (z >> np.uint64(31))
+
+  def uniform(self, lo=0.0, hi=1.0, size=()) -> np.ndarray:
+    n = int(np.prod(size)) if size != () else 1
+    u = (self._u64(n) >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+    return (lo + (hi - lo) * u).reshape(size)
+
+  def standard_normal(self, size=()) -> np.ndarray:
+    n = int(np.prod(size)) if size != () else 1
+    z = self._u64(n)
+    s = np.zeros(n, np.int64)
+    for k in range(4):
+      s += ((z >> np.uint64(16 * k)) & np.uint64(0xFFFF)).astype(np.int64)
+    # sum of four U{0..65535}: mean 131070, variance 4 * (65536^2 - 1) / 12
+    return ((s - 131070).astype(np.float64) / 37837.22713327866).reshape(size)
+
+  def poisson15(self, size=()) -> np.ndarray:
+    n = int(np.prod(size)) if size != () else 1
+    r = self._u64(n) >> np.uint64(11)                     # 53-bit
+    # floor(CDF_Poisson(0.15)(k) * 2^53), k = 0..3
+    t = np.array([7752568243805408, 8915453480376219, 9002669873119030, 9007030692756171], np.uint64)
+    k = (r >= t[0]).astype(np.uint8) + (r >= t[1]) + (r >= t[2]) + (r >= t[3])
+    return k.astype(np.uint8).reshape(size)
+
+  def integers(self, lo: int, hi: int, size=()) -> np.ndarray:
+    n = int(np.prod(size)) if size != () else 1
+    return (lo + (self._u64(n) >> np.uint64(33)).astype(np.int64) % (hi - lo)).reshape(size)
+
+
 def _effective_energy(kernel, a, mask, bits):
   """sum_k w_eff[k, n]^2 per output channel of the quantized + masked kernel
   (synthetic-statistics helper only; the product quantizes on the device)."""
@@ -78,8 +125,10 @@ def kernel_shapes(T: int, channels: int, num_classes: int, H: int
 
 def make_variables(bits: int = 8, prune_percentage: float = 0.5, T: int = 20,
                    channels: int = 128, num_classes: int = 11, H: int = 128,
-                   seed: int = 1, prune_global: bool = True) -> Dict:
-  rng = np.random.default_rng(seed)
+                   seed: int = 1, prune_global: bool = True, stable: bool = False) -> Dict:
+  """``stable=True`` draws from :class:`StableRNG` (version-independent streams; used by
+  the from-reference fixtures), otherwise from ``np.random.default_rng``."""
+  rng = StableRNG(seed) if stable else np.random.default_rng(seed)
   shapes = kernel_shapes(T, channels, num_classes, H)
   kernels = OrderedDict()
   for name, shp in shapes.items():
@@ -107,19 +156,22 @@ def make_variables(bits: int = 8, prune_percentage: float = 0.5, T: int = 20,
     C = channels
     lay = params[_CONV_NAMES[i]]
     energy = _effective_energy(lay["kernel"], lay["DuQ_0"]["a"][0], lay["prune_0"]["mask"], bits)
-    var = np.maximum(_IN_M2[i] * energy, 1e-6) * rng.uniform(0.8, 1.25, C)
+    var = np.maximum(_IN_M2[i] * energy, 1e-6) * rng.uniform(0.8, 1.25, (C,))
     params[f"BatchNorm_{i}"] = {
-        "scale": rng.uniform(0.8, 1.2, C).astype(F32),
-        "bias": (0.5 + 0.1 * rng.standard_normal(C)).astype(F32)}
+        "scale": rng.uniform(0.8, 1.2, (C,)).astype(F32),
+        "bias": (0.5 + 0.1 * rng.standard_normal((C,))).astype(F32)}
     stats[f"BatchNorm_{i}"] = {
-        "mean": (0.05 * np.sqrt(var) * rng.standard_normal(C)).astype(F32),
+        "mean": (0.05 * np.sqrt(var) * rng.standard_normal((C,))).astype(F32),
         "var": var.astype(F32)}
   return {"params": params, "batch_stats": stats}
 
 
 def make_frames(B: int, T: int = 20, H: int = 128, W: int = 128, seed: int = 0,
-                rate: float = 0.15) -> np.ndarray:
+                rate: float = 0.15, stable: bool = False) -> np.ndarray:
   """uint8 event-count frames (B,T,H,W,2)."""
+  if stable:
+    assert rate == 0.15
+    return StableRNG(seed).poisson15((B, T, H, W, 2))
   rng = np.random.default_rng(seed)
   return np.minimum(rng.poisson(rate, size=(B, T, H, W, 2)), 15).astype(np.uint8)
 
