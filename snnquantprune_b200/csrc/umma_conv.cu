@@ -41,16 +41,15 @@ constexpr int kTmemCols = 512;
 // SS-mode MMA pulls (128 + 144) * 32 B from shared memory per 72 cycles (94 % of the 128 B/cycle port, measured
 // tensor pipe 57 % active); reading A from TMEM leaves 64 B/cycle.  TMEM budget: 2 x 144 accumulator columns +
 // 7 taps x 4 K-steps x 8 columns = 512 exactly.  The last two taps stay in shared memory (32 KB).
-constexpr int kTmemTaps = 7, kSmemTaps = 9 - kTmemTaps;
-constexpr int kWSmemBytes = kSmemTaps * kTapBytes;   // 32768
+// (template parameters TT = taps in TMEM, ST = input ring depth; production 7 / 4.  Other splits exist to measure
+// how much of the TMEM the layer really needs: tools/time_conv2_variants.py, profiles/r2_conv2_tmem_split.txt)
 constexpr int kAccStride = 144;                 // TMEM column offset of accumulator buffer 1
 constexpr int kACol0 = 2 * kAccStride;          // first TMEM column of the resident weights
-constexpr int kStages = 4;                      // input ring depth (the freed shared memory)
+constexpr int smem_bytes_for(int tt, int st) { return (9 - tt) * kTapBytes + st * kStageBytes + 1024 /*barriers*/ + 1024 /*align slack*/; }
 // Fast-epilogue flavour.  The packed f32x2 form converts with the magic-number trick, exact only for
 // |acc| < 2^22 ({0,1} inputs); the scalar form (I2FP) is exact for any uint8 input.  This kernel is bound by
 // the tensor pipe (97 % active), so the always-exact scalar form is the default.
 constexpr bool kPackedMath = false;
-constexpr int kSmemBytes = kWSmemBytes + kStages * kStageBytes + 1024 /*barriers*/ + 1024 /*align slack*/;
 
 struct UmmaArgs {
   int T, B, H, W;
@@ -80,10 +79,11 @@ template <> struct Cfg<16> { static constexpr int TH = 8, R = 4, WC = 16; };
 
 // FAST: standard LIF constants (tau 2, threshold 1, reset 0), pooled output, no
 // instrumentation outputs -- the production variant; !FAST handles everything else.
-template <int WCFG, bool FAST, bool COUNTS>
+template <int WCFG, bool FAST, bool COUNTS, int kTmemTaps = 7, int kStages = 4>
 __global__ void __launch_bounds__(kThreads, 1)
 k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                const UmmaArgs a) {
+  constexpr int kWSmemBytes = (9 - kTmemTaps) * kTapBytes;
   using CF = Cfg<WCFG>;
   constexpr int TH = CF::TH, R = CF::R, WC = CF::WC;
   extern __shared__ uint8_t smem_raw[];
@@ -125,7 +125,7 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   if (warp == kEpiWarps) {
     // ===================== TMA producer =====================
     if (ptx::elect_one()) {
-      ptx::mbar_expect_tx(w_full, kWSmemBytes);
+      if (kWSmemBytes) ptx::mbar_expect_tx(w_full, kWSmemBytes); else ptx::mbar_arrive(w_full);
       for (int tap = kTmemTaps; tap < 9; ++tap)
         ptx::tma_load_2d(w_smem + (tap - kTmemTaps) * kTapBytes, &tmap_w, w_full, 0, tap * kC);
       uint32_t step = 0;
@@ -221,7 +221,8 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     {
       // one-time: this thread's weight row (output channel c) of the TMEM-resident taps -> tensor memory.
       // A-operand layout: lane = row, 32-bit column j of a K-step holds K bytes 4j .. 4j+3.
-      const int tap0 = g == 0 ? 0 : 4, tap1 = g == 0 ? 4 : kTmemTaps;
+      constexpr int kSplit = kTmemTaps < 4 ? kTmemTaps : 4;
+      const int tap0 = g == 0 ? 0 : kSplit, tap1 = g == 0 ? kSplit : kTmemTaps;
       for (int tap = tap0; tap < tap1; ++tap) {
         const int4 *wrow = reinterpret_cast<const int4 *>(a.wq + ((int64_t)tap * kC + c) * kC);
 #pragma unroll
@@ -476,12 +477,34 @@ int launch_conv3x3_umma(const snnqp_block_params &p, const uint8_t *x, const int
 
   const int grid = a.total_items < sm_count() ? a.total_items : sm_count();
   const bool fast = p.tau == 2.0f && p.v_threshold == 1.0f && p.v_reset == 0.0f && p.pool && !u_final && !acc_dump;
+  constexpr int kSmemBytes = smem_bytes_for(7, 4);
 #define SNNQP_LAUNCH_UMMA(WV, FA, CO)                                                                          \
   do {                                                                                                         \
     SNNQP_CUDA(cudaFuncSetAttribute(k_conv3x3_umma<WV, FA, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                     kSmemBytes));                                                              \
     k_conv3x3_umma<WV, FA, CO><<<grid, kThreads, kSmemBytes, st>>>(tmx, tmw, a);                               \
   } while (0)
+#define SNNQP_LAUNCH_UMMA_X(TT, ST)                                                                            \
+  do {                                                                                                         \
+    SNNQP_CUDA(cudaFuncSetAttribute(k_conv3x3_umma<64, true, false, TT, ST>,                                   \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(TT, ST)));     \
+    k_conv3x3_umma<64, true, false, TT, ST><<<grid, kThreads, smem_bytes_for(TT, ST), st>>>(tmx, tmw, a);      \
+  } while (0)
+  // developer experiment (tools/time_conv2_variants.py): other TMEM / shared-memory splits of the W = 64 block
+  static const int split_env = getenv("SNNQP_C2_SPLIT") ? atoi(getenv("SNNQP_C2_SPLIT")) : 0;   // TT * 10 + ST
+  if (split_env && p.W == 64 && fast && !counts) {
+    switch (split_env) {
+      case 72: SNNQP_LAUNCH_UMMA_X(7, 2); break;
+      case 52: SNNQP_LAUNCH_UMMA_X(5, 2); break;
+      case 42: SNNQP_LAUNCH_UMMA_X(4, 2); break;
+      case 32: SNNQP_LAUNCH_UMMA_X(3, 2); break;
+      case 33: SNNQP_LAUNCH_UMMA_X(3, 3); break;
+      case 2: SNNQP_LAUNCH_UMMA_X(0, 2); break;
+      default: return invalid("SNNQP_C2_SPLIT: unknown split %d", split_env);
+    }
+    SNNQP_POST_LAUNCH("k_conv3x3_umma");
+    return SNNQP_OK;
+  }
 #define SNNQP_LAUNCH_UMMA_W(WV)                                             \
   do {                                                                      \
     if (!fast) SNNQP_LAUNCH_UMMA(WV, false, false);                         \

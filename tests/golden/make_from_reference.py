@@ -177,6 +177,20 @@ def ops_fixture(quant, sl, flax_qconv, flax_qdense):
     fx[f"lif{ci}_x"], fx[f"lif{ci}_u0"] = x, u0
     fx[f"lif{ci}_u"], fx[f"lif{ci}_s"] = np.stack(us), np.stack(ss).astype(np.uint8)
     lif_cases.append({"tau": tau, "v_threshold": vth, "v_reset": vr})
+  # LIF on a grid of exactly representable pre-activations x = count * 2^-6 - 0.25 (count = uint8): a fused GPU
+  # block with an identity centre tap reproduces exactly these x, so its LIF can be held to the reference's
+  # bit for bit (folded fmaf == unfused multiply-add on this grid).  Layout (T, B=1, H=8, W=16, C=128).
+  cnt = rng.integers(0, 256, (8, 1, 8, 16, 128)).astype(np.uint8)
+  cnt[:, :, :, :, :8] = np.minimum(cnt[:, :, :, :, :8], 90)          # some channels stay mostly sub-threshold
+  xg = (cnt.astype(F32) * F32(2.0 ** -6) - F32(0.25)).astype(F32)
+  mod = sl.multi_step_LIF(tau=2.0, spike_fn=sl.atan)
+  u = np.zeros(xg.shape[1:], F32)
+  sg = []
+  for t in range(xg.shape[0]):
+    u, s_ = mod.apply({}, u.copy(), xg[t])
+    sg.append(s_)
+  fx["lifgrid_counts"], fx["lifgrid_uT"] = cnt, u
+  fx["lifgrid_bits"] = np.packbits(np.stack(sg).astype(np.uint8).reshape(-1))
   # QuantConv / QuantDense standalone (layer facades): 3x3 pad 1, 1-D k=4 'SAME', dense
   cfg = ml_collections.ConfigDict()
   cfg.bits = 4

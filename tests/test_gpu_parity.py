@@ -472,20 +472,24 @@ def test_network_against_golden_fixture(cuda_lib, name):
   import sys
   sys.path.insert(0, GOLD)
   import make_golden
-  if make_golden.variables_digest(v) != m["variables_sha"] or make_golden.sha(fr) != m["frames_sha"]:
-    pytest.skip("numpy RNG stream differs from the one the fixture was made with")
+  # same image on the GPU box: a different stream is a broken environment, not a reason to skip
+  assert make_golden.variables_digest(v) == m["variables_sha"] and make_golden.sha(fr) == m["frames_sha"], \
+      "numpy RNG stream differs from the one the fixture was made with"
   c = {}
   logits = engine_for(v, m["bits"], m["T"], m["H"]).forward(dev(fr), collect=c).cpu().numpy()
   for k in ("s1", "s2", "s3", "s4"):          # integer-input layers: bit-exact
     got = np.swapaxes(c[k].cpu().numpy(), 0, 1)
     assert np.array_equal(np.packbits(got.reshape(-1)), z[k + "_bits"]), k
   assert np.max(np.abs(np.swapaxes(c["att4"].cpu().numpy(), 0, 1) - z["att4"]) / z["att4"]) <= 2e-6
+  nflip = 0
   for k in ("s5", "d1", "d2"):                # downstream of expf / fp32 sums: flip budget
     got = np.swapaxes(c[k].cpu().numpy(), 0, 1).reshape(-1)
     ref = np.unpackbits(z[k + "_bits"])[:got.size]
     assert np.mean(got != ref) <= 1e-4, k
-  assert np.max(np.abs(logits - z["logits_int"])) <= 1e-2
-  assert np.max(np.abs(logits - z["logits_float"])) <= 1e-2
+    nflip += int((got != ref).sum())
+  tol = 1e-6 + min(nflip, 16) / (m["T"] * 10)   # one flipped output spike = 1 / (T * 10) of a logit
+  assert np.max(np.abs(logits - z["logits_int"])) <= tol
+  assert np.max(np.abs(logits - z["logits_float"])) <= tol
 
 
 def test_network_layerwise_teacher_forced_and_float_path(cuda_lib, oracle_lib):
@@ -517,14 +521,18 @@ def test_network_layerwise_teacher_forced_and_float_path(cuda_lib, oracle_lib):
   # reference-order float path, free running
   cf = {}
   lf = ref_snn.cextnet_forward(v, fr, bits, collect=cf)
+  nflip = 0
   for k, kf in (("s1", "pool1"), ("s2", "pool2"), ("s3", "pool3"), ("s4", "conv4_spikes"),
                 ("s5", "conv5_spikes"), ("d1", "dense1_spikes"), ("d2", "dense2_spikes")):
-    assert np.mean(tb(k) != (cf[kf] != 0)) <= 1e-4, k
+    d = tb(k) != (cf[kf] != 0)
+    assert np.mean(d) <= 1e-4, k
+    nflip += int(d.sum())
   for i in range(1, 6):
     ug, uf = c[f"conv{i}_u"].cpu().numpy(), cf[f"conv{i}_u"]
-    rel = np.abs(ug - uf) / np.maximum(np.abs(uf), 1.0)
-    assert np.quantile(rel, 0.9999) <= 1e-5, i
-  assert np.max(np.abs(logits - lf)) <= 1e-2
+    bad = np.abs(ug - uf) > 1e-5 * np.maximum(np.abs(uf), 1.0)
+    # every neuron within 1e-5 unless a counted flip sits upstream of it (3x3xC fan-out per layer and step)
+    assert bad.sum() <= 2048 * nflip, (i, int(bad.sum()), nflip)
+  assert np.max(np.abs(logits - lf)) <= 1e-6 + min(nflip, 16) / (T * 10)
 
 
 def test_config3_T10_ten_classes(cuda_lib, oracle_lib):
@@ -546,7 +554,7 @@ def test_config3_T10_ten_classes(cuda_lib, oracle_lib):
     assert np.array_equal(tb(k), co[k]), k
   assert np.array_equal(tb("d2"), co["d2"]) and np.array_equal(logits, lo)
   lf = ref_snn.cextnet_forward(v, fr, bits)
-  assert np.max(np.abs(logits - lf)) <= 1e-2
+  assert np.max(np.abs(logits - lf)) <= 2.0 / (T * 10)
   assert np.array_equal(eng.forward(dev(fr)).cpu().numpy(), logits)      # production path, same logits
 
 
