@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define SNNQP_ABI_VERSION 1
+#define SNNQP_ABI_VERSION 2
 
 #define SNNQP_OK 0
 #define SNNQP_ERR_INVALID 1      /* bad argument / unsupported shape           */
@@ -126,7 +126,32 @@ typedef struct snnqp_block_params {
   float tau, v_threshold, v_reset; /* multi_step_LIF, spiking_learning.py:390-397 */
   int32_t pool;            /* 1: fuse the 2x2/2 max-pool (models.py:145-147)      */
   int32_t impl;            /* SNNQP_IMPL_*                                        */
+  int32_t x_format;        /* SNNQP_SPIKES_*: layout of x (BITS: binary inputs, Cin % 32 == 0) */
+  int32_t y_format;        /* SNNQP_SPIKES_*: layout of the emitted spikes        */
+  int32_t lif_mode;        /* SNNQP_LIF_*                                          */
 } snnqp_block_params;
+
+/* Spike tensor layouts (both channel-minor, strides in bytes):
+ *   U8   one byte per spike / event count: [..][H][W][C] uint8;
+ *   BITS bit-packed {0,1} spikes: [..][H][W][C/8] bytes, channel c = bit (c & 7)
+ *        of byte (c >> 3) (= bit c % 32 of little-endian word c / 32), i.e.
+ *        numpy.packbits(..., axis=-1, bitorder="little").  The reference's
+ *        spikes are fp32 {0,1} (spiking_learning.py:412-416); 8x fewer bytes
+ *        than U8, 32x fewer than fp32.  Emitted by the production epilogues
+ *        (pool == 1, no instrumentation outputs) with one 32-channel word per
+ *        warp ballot; consumed by the tcgen05 3x3 block, whose expander warps
+ *        turn the TMA-staged bits into the u8 MMA operand in shared memory. */
+#define SNNQP_SPIKES_U8 0
+#define SNNQP_SPIKES_BITS 1
+/* LIF arithmetic for tau = 2, v_threshold = 1, v_reset = 0 (other constants
+ * always use the reference's op order):
+ *   EXACT  u + (x - u) / 2 in the reference's op order (spiking_learning.py:409),
+ *          bit-identical to the oracle;
+ *   FAST   fma(u, 0.5, x / 2) with the halving folded into scale / bias: one
+ *          rounding instead of two, |du| <= 1 ulp per step (north-star bar
+ *          1e-5), spikes may flip only when un is within an ulp of 1. */
+#define SNNQP_LIF_EXACT 0
+#define SNNQP_LIF_FAST 1
 
 /* SpikingBlock(QuantConv 3x3 pad 1, BatchNorm, multi_step_LIF) over T steps
  * with zero initial carry (spiking_learning.py:441-472), optionally followed
@@ -231,6 +256,11 @@ int snnqp_events_to_frames(const int32_t *addrs, const int64_t *offsets, int B,
  * counts[i] = number of non-zero bytes of slice i (slice_bytes long, slices
  * stride_slice apart).  counts is zeroed by the call. */
 int snnqp_slice_nonzeros(const uint8_t *x, int n_slices, int64_t slice_bytes,
+                         int64_t stride_slice, int32_t *counts, void *stream);
+
+/* Same for a bit-packed spike tensor (SNNQP_SPIKES_BITS): counts[s] = set bits
+ * of slice s -- the same numerator, one eighth of the bytes. */
+int snnqp_slice_popcount(const uint8_t *x, int n_slices, int64_t slice_bytes,
                          int64_t stride_slice, int32_t *counts, void *stream);
 
 /* Diagnostic (no reference counterpart): dense int8 tensor-pipe ceiling of the

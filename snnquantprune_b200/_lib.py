@@ -11,7 +11,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # SNNQP_LIB: developer switch for same-box A/B timing of two builds (tools/); the product path is the in-tree .so
 LIB_PATH = os.environ.get("SNNQP_LIB") or os.path.join(_HERE, "libsnnqp.so")
 
+ABI_VERSION = 2          # include/snnqp.h SNNQP_ABI_VERSION (block params carry x_format / y_format / lif_mode)
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
+SPIKES_U8, SPIKES_BITS = 0, 1
+LIF_EXACT, LIF_FAST = 0, 1
 
 
 class SnnqpError(RuntimeError):
@@ -30,6 +33,7 @@ class BlockParams(C.Structure):
       ("att_mod", C.c_int32),
       ("tau", C.c_float), ("v_threshold", C.c_float), ("v_reset", C.c_float),
       ("pool", C.c_int32), ("impl", C.c_int32),
+      ("x_format", C.c_int32), ("y_format", C.c_int32), ("lif_mode", C.c_int32),
   ]
 
 
@@ -60,6 +64,7 @@ SIGNATURES = {
     "snnqp_eval_metrics": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "snnqp_events_to_frames": (_i, [_vp, _vp, _i, _i, _i, _i, _i64, _vp, _i, _vp, _vp]),
     "snnqp_slice_nonzeros": (_i, [_vp, _i, _i64, _i64, _vp, _vp]),
+    "snnqp_slice_popcount": (_i, [_vp, _i, _i64, _i64, _vp, _vp]),
     "snnqp_diag_imma_peak": (_i, [_i, _i, C.POINTER(C.c_double), _vp]),
 }
 
@@ -78,7 +83,7 @@ def lib() -> C.CDLL:
       fn = getattr(l, name)
       fn.restype = res
       fn.argtypes = args
-    if l.snnqp_abi_version() != 1:
+    if l.snnqp_abi_version() != ABI_VERSION:
       raise RuntimeError("libsnnqp.so ABI version mismatch")
     _lib = l
   return _lib

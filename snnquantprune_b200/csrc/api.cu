@@ -50,7 +50,18 @@ static int check_conv(const snnqp_block_params *p, const void *x, const void *wq
   if (p->Cout % 32 != 0 || p->Cout > 128 || p->Cout <= 0)
     return unsupported("%s: Cout=%d (supported: multiples of 32 up to 128)", fn, p->Cout);
   if (!(p->tau > 0.f)) return invalid("%s: tau=%f must be > 0", fn, (double)p->tau);
+  if ((unsigned)p->x_format > SNNQP_SPIKES_BITS || (unsigned)p->y_format > SNNQP_SPIKES_BITS)
+    return invalid("%s: x_format=%d y_format=%d (SNNQP_SPIKES_U8 / SNNQP_SPIKES_BITS)", fn, p->x_format, p->y_format);
+  // 101..103: developer selection of one single-rounding variant (tests / tools); SNNQP_LIF_FAST = the library's pick
+  if ((unsigned)p->lif_mode > SNNQP_LIF_FAST && !(p->lif_mode >= 101 && p->lif_mode <= 103))
+    return invalid("%s: lif_mode=%d", fn, p->lif_mode);
   return SNNQP_OK;
+}
+static bool any_bits(const snnqp_block_params *p) {
+  return p->x_format == SNNQP_SPIKES_BITS || p->y_format == SNNQP_SPIKES_BITS;
+}
+static int bits_need_tcgen05(const char *what) {
+  return unsupported("snnqp_spiking_conv3x3_fwd: bit-packed spikes are implemented by the tcgen05 kernels only (%s)", what);
 }
 }  // namespace snnqp
 
@@ -85,9 +96,11 @@ int snnqp_spiking_conv3x3_counts_fwd(const snnqp_block_params *p, const uint8_t 
       return launch_conv1_umma(*p, x, wq + (int64_t)p->Cout * 32, scale, bias, spikes, u_final, (int32_t *)acc_dump, st);
     }
     if (impl != SNNQP_IMPL_SIMT) return invalid("snnqp_spiking_conv3x3_fwd: impl=%d", p->impl);
+    if (any_bits(p)) return bits_need_tcgen05("conv1 outside the tcgen05 envelope or SNNQP_IMPL_SIMT");
     return launch_conv3x3_simt(*p, x, att, wq, scale, bias, spikes, u_final, acc_dump, nullptr, nullptr, st);
   }
   if (att) {
+    if (any_bits(p)) return unsupported("snnqp_spiking_conv3x3_fwd: att-weighted block takes and emits SNNQP_SPIKES_U8");
     // real-valued input att * x: three byte-plane int8 contractions on tcgen05, or fp32 FMAs (SIMT)
     if (impl == SNNQP_IMPL_AUTO) impl = umma_conv_att_supported(*p, att) ? SNNQP_IMPL_TCGEN05 : SNNQP_IMPL_SIMT;
     if (impl == SNNQP_IMPL_TCGEN05) {
@@ -109,6 +122,7 @@ int snnqp_spiking_conv3x3_counts_fwd(const snnqp_block_params *p, const uint8_t 
     return launch_conv3x3_umma(*p, x, wq, scale, bias, spikes, u_final, (int32_t *)acc_dump, spike_counts, st);
   }
   if (impl != SNNQP_IMPL_SIMT) return invalid("snnqp_spiking_conv3x3_fwd: impl=%d", p->impl);
+  if (any_bits(p)) return bits_need_tcgen05("shape outside the tcgen05 envelope or SNNQP_IMPL_SIMT");
   return launch_conv3x3_simt(*p, x, att, wq, scale, bias, spikes, u_final, acc_dump, nullptr, spike_counts, st);
 }
 
@@ -117,6 +131,7 @@ int snnqp_qconv3x3_fwd(const snnqp_block_params *p, const uint8_t *x, const int8
   if (int rc = require_device()) return rc;
   if (int rc = check_conv(p, x, wq, scale, bias, "snnqp_qconv3x3_fwd")) return rc;
   if (!y) return invalid("snnqp_qconv3x3_fwd: null output");
+  if (any_bits(p)) return unsupported("snnqp_qconv3x3_fwd: SNNQP_SPIKES_U8 input only");
   return launch_conv3x3_simt(*p, x, nullptr, wq, scale, bias, nullptr, nullptr, nullptr, y, nullptr,
                              (cudaStream_t)stream);
 }
@@ -129,6 +144,8 @@ int snnqp_spiking_dense_fwd(const snnqp_block_params *p, const uint8_t *x, const
   if (p->T <= 0 || p->B <= 0 || p->Cin <= 0 || p->Cout <= 0)
     return invalid("snnqp_spiking_dense_fwd: bad shape T=%d B=%d K=%d N=%d", p->T, p->B, p->Cin, p->Cout);
   if (!(p->tau > 0.f)) return invalid("snnqp_spiking_dense_fwd: tau must be > 0");
+  if (p->x_format != SNNQP_SPIKES_U8 || p->y_format != SNNQP_SPIKES_U8)
+    return unsupported("snnqp_spiking_dense_fwd: SNNQP_SPIKES_U8 only");
   const int k_pad = (p->Cin + 15) / 16 * 16;
   if (k_pad > 8192) return unsupported("snnqp_spiking_dense_fwd: K=%d too large (max 8192)", p->Cin);
   if (att && p->att_mod <= 0) return invalid("snnqp_spiking_dense_fwd: att_mod=%d", p->att_mod);

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 OUT = os.path.join(os.path.dirname(HERE), "libsnnqp.so")
 SOURCES = ["runtime.cu", "pack.cu", "simt.cu", "umma_conv.cu", "umma_conv1.cu", "umma_att.cu", "diag.cu", "frames.cu", "api.cu"]
-HEADERS = ["common.cuh", "ptx.cuh", os.path.join(ROOT, "include", "snnqp.h")]
+HEADERS = ["common.cuh", "ptx.cuh", "tmap.cuh", "epilogue.cuh", os.path.join(ROOT, "include", "snnqp.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

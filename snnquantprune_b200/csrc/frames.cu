@@ -79,6 +79,8 @@ k_events_to_frames(const int32_t *__restrict__ addrs, const int64_t *__restrict_
 }
 
 // grid: (blocks_per_slice, n_slices); 16 bytes per thread per iteration
+// BITS: the tensor is bit-packed spikes (SNNQP_SPIKES_BITS): count set bits instead of non-zero bytes
+template <bool BITS>
 __global__ void __launch_bounds__(256)
 k_slice_nonzeros(const uint8_t *__restrict__ x, int64_t slice_bytes, int64_t stride_slice, int vec16,
                  int32_t *__restrict__ counts) {
@@ -89,10 +91,10 @@ k_slice_nonzeros(const uint8_t *__restrict__ x, int64_t slice_bytes, int64_t str
   for (int64_t i = tid; i < n16; i += nthr) {
     const uint4 v = __ldg(reinterpret_cast<const uint4 *>(base) + i);
     // non-zero bytes of a word: bit 7 of ((b & 0x7F) + 0x7F) | b, per byte
-    auto nzb = [](uint32_t w) { return __popc(((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu | w) & 0x80808080u); };
+    auto nzb = [](uint32_t w) { return BITS ? __popc(w) : __popc(((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu | w) & 0x80808080u); };
     c += nzb(v.x) + nzb(v.y) + nzb(v.z) + nzb(v.w);
   }
-  for (int64_t i = n16 * 16 + tid; i < slice_bytes; i += nthr) c += base[i] != 0;
+  for (int64_t i = n16 * 16 + tid; i < slice_bytes; i += nthr) c += BITS ? __popc((uint32_t)base[i]) : (base[i] != 0);
   for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(counts + blockIdx.y, c);
 }
@@ -138,8 +140,8 @@ extern "C" int snnqp_events_to_frames(const int32_t *addrs, const int64_t *offse
                 : launch_events<uint8_t, false>(addrs, offsets, B, T, wh, resolution_scale, f, ns, st);
 }
 
-extern "C" int snnqp_slice_nonzeros(const uint8_t *x, int n_slices, int64_t slice_bytes, int64_t stride_slice,
-                                    int32_t *counts, void *stream_) {
+static int slice_count(const uint8_t *x, int n_slices, int64_t slice_bytes, int64_t stride_slice, int32_t *counts,
+                       bool bits, void *stream_) {
   using namespace snnqp;
   if (int r = require_device()) return r;
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
@@ -152,11 +154,25 @@ extern "C" int snnqp_slice_nonzeros(const uint8_t *x, int n_slices, int64_t slic
   bx = bx < 1 ? 1 : (bx > cap ? (cap < 1 ? 1 : cap) : bx);
   for (int s0 = 0; s0 < n_slices; s0 += 65535) {                         // gridDim.y limit
     const int ns = n_slices - s0 < 65535 ? n_slices - s0 : 65535;
-    k_slice_nonzeros<<<dim3(bx, ns), 256, 0, st>>>(x + (int64_t)s0 * stride_slice, slice_bytes, stride_slice, vec16,
-                                                    counts + s0);
+    if (bits)
+      k_slice_nonzeros<true><<<dim3(bx, ns), 256, 0, st>>>(x + (int64_t)s0 * stride_slice, slice_bytes, stride_slice, vec16,
+                                                           counts + s0);
+    else
+      k_slice_nonzeros<false><<<dim3(bx, ns), 256, 0, st>>>(x + (int64_t)s0 * stride_slice, slice_bytes, stride_slice, vec16,
+                                                            counts + s0);
     count_launch();
   }
-  if (cudaError_t e = cudaGetLastError()) return cuda_fail(e, "k_slice_nonzeros");
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "k_slice_nonzeros");
   return SNNQP_OK;
 }
 
+extern "C" int snnqp_slice_nonzeros(const uint8_t *x, int n_slices, int64_t slice_bytes, int64_t stride_slice,
+                                    int32_t *counts, void *stream_) {
+  return slice_count(x, n_slices, slice_bytes, stride_slice, counts, false, stream_);
+}
+
+extern "C" int snnqp_slice_popcount(const uint8_t *x, int n_slices, int64_t slice_bytes, int64_t stride_slice,
+                                    int32_t *counts, void *stream_) {
+  return slice_count(x, n_slices, slice_bytes, stride_slice, counts, true, stream_);
+}

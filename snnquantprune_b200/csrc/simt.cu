@@ -42,7 +42,9 @@ k_conv3x3_simt(const snnqp_block_params p, const uint8_t *__restrict__ x,
   const float sc = scale[o], bi = bias[o];
   const int Ho = p.pool ? QH : H, Wo = p.pool ? QW : W;
 
-  for (int64_t quad = (int64_t)blockIdx.x * nlane + lane_q; quad < total;
+  // threads beyond nlane * Cout (Cout does not divide the block, e.g. 96) would redo the next block's quad 0
+  // and double-count its spikes: they only helped staging the weights
+  for (int64_t quad = lane_q < nlane ? (int64_t)blockIdx.x * nlane + lane_q : total; quad < total;
        quad += (int64_t)gridDim.x * nlane) {
     const int qw = (int)(quad % QW), qh = (int)((quad / QW) % QH), b = (int)(quad / ((int64_t)QW * QH));
     float u[4] = {0.f, 0.f, 0.f, 0.f};
@@ -157,7 +159,9 @@ k_conv3x3_c2_simt(const snnqp_block_params p, const uint8_t *__restrict__ x,
   const float sc = scale[o], bi = bias[o];
   const int Ho = p.pool ? QH : H, Wo = p.pool ? QW : W;
   (void)Ho;
-  for (int64_t quad = (int64_t)blockIdx.x * nlane + lane_q; quad < total;
+  // threads beyond nlane * Cout (Cout does not divide the block, e.g. 96) would redo the next block's quad 0
+  // and double-count its spikes: they only helped staging the weights
+  for (int64_t quad = lane_q < nlane ? (int64_t)blockIdx.x * nlane + lane_q : total; quad < total;
        quad += (int64_t)gridDim.x * nlane) {
     const int qw = (int)(quad % QW), qh = (int)((quad / QW) % QH), b = (int)(quad / ((int64_t)QW * QH));
     float u[4] = {0.f, 0.f, 0.f, 0.f};

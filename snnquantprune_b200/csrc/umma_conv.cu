@@ -25,10 +25,18 @@
 #include "common.cuh"
 #include "epilogue.cuh"
 #include "ptx.cuh"
+#include "tmap.cuh"
 
 namespace snnqp {
 
 namespace {
+
+// timing-bisection switches exist only in SNNQP_BISECT builds (tools/): never in the shipped hot loops
+#ifdef SNNQP_C1_BISECT
+#define UMMA_DBG(bit) (a.debug & (bit))
+#else
+#define UMMA_DBG(bit) false
+#endif
 
 constexpr int kC = 128;
 constexpr int kWBytes = 9 * kC * kC;            // 147456
@@ -36,6 +44,11 @@ constexpr int kTapBytes = kC * kC;              // 16384
 constexpr int kStageBytes = 35840;              // >= (2P+2+N) rows * 128 B for every config, 1024-aligned
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = (kEpiWarps + 2) * 32;  // + TMA warp + MMA warp
+// Bit-packed input (SNNQP_SPIKES_BITS): TMA stages the packed tile (16 B per position), two expander warps turn
+// bits into the u8 K-major 128B-swizzled MMA operand (3 integer ops per 4 bytes: nibble * 0x00204081 & 0x01010101).
+constexpr int kExpWarps = 2;
+constexpr int kThreadsX = kThreads + kExpWarps * 32;
+constexpr int kPkStages = 4, kPkStageBytes = 4352;   // >= (TH+2) * (W+2) * 16 B for every config, 128-aligned
 constexpr int kTmemCols = 512;
 // Weights (A operand) of the first kTmemTaps taps live in TENSOR MEMORY for the CTA's lifetime: with N = 144 an
 // SS-mode MMA pulls (128 + 144) * 32 B from shared memory per 72 cycles (94 % of the 128 B/cycle port, measured
@@ -45,7 +58,9 @@ constexpr int kTmemCols = 512;
 // how much of the TMEM the layer really needs: tools/time_conv2_variants.py, profiles/r2_conv2_tmem_split.txt)
 constexpr int kAccStride = 144;                 // TMEM column offset of accumulator buffer 1
 constexpr int kACol0 = 2 * kAccStride;          // first TMEM column of the resident weights
-constexpr int smem_bytes_for(int tt, int st) { return (9 - tt) * kTapBytes + st * kStageBytes + 1024 /*barriers*/ + 1024 /*align slack*/; }
+constexpr int smem_bytes_for(int tt, int st, bool xbits = false) {
+  return (9 - tt) * kTapBytes + st * kStageBytes + (xbits ? kPkStages * kPkStageBytes : 0) + 1024 /*barriers*/ + 1024 /*align slack*/;
+}
 // Fast-epilogue flavour.  The packed f32x2 form converts with the magic-number trick, exact only for
 // |acc| < 2^22 ({0,1} inputs); the scalar form (I2FP) is exact for any uint8 input.  This kernel is bound by
 // the tensor pipe (97 % active), so the always-exact scalar form is the default.
@@ -61,6 +76,8 @@ struct UmmaArgs {
   int base_off_mode;
   int tb_swapped;            // tensor-map dims 3/4 are (b, t) instead of (t, b)
   int one;                   // always 1 (runtime operand of the magic-number IMAD, see epilogue.cuh)
+  int y_bits;                // 1: emit bit-packed spikes (production variants only)
+  int box_rows;              // (TH + 2) * P: positions of one input box
   int debug;                 // SNNQP_UMMA_DEBUG: bit0 skip MMA issue, bit1 skip epilogue math (timing bisection only)
   uint32_t stage_tx_bytes;
   const float *scale, *bias;
@@ -79,8 +96,8 @@ template <> struct Cfg<16> { static constexpr int TH = 8, R = 4, WC = 16; };
 
 // FAST: standard LIF constants (tau 2, threshold 1, reset 0), pooled output, no
 // instrumentation outputs -- the production variant; !FAST handles everything else.
-template <int WCFG, bool FAST, bool COUNTS, int kTmemTaps = 7, int kStages = 4>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int WCFG, bool FAST, bool COUNTS, int kTmemTaps = 7, int kStages = 4, bool XBITS = false>
+__global__ void __launch_bounds__(XBITS ? kThreadsX : kThreads, 1)
 k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                const UmmaArgs a) {
   constexpr int kWSmemBytes = (9 - kTmemTaps) * kTapBytes;
@@ -90,14 +107,17 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t *w_smem = smem;
   uint8_t *stage_smem = smem + kWSmemBytes;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kWSmemBytes + kStages * kStageBytes);
+  uint8_t *pk_smem = stage_smem + kStages * kStageBytes;          // XBITS: packed-tile ring
+  uint64_t *bars = reinterpret_cast<uint64_t *>(pk_smem + (XBITS ? kPkStages * kPkStageBytes : 0));
   uint64_t *w_full = bars + 0;
   uint64_t *a_ready = bars + 1;                 // weights stored to TMEM by the epilogue warps
   uint64_t *in_full = bars + 2;                 // [kStages]
   uint64_t *in_empty = in_full + kStages;       // [kStages]
   uint64_t *acc_full = in_empty + kStages;      // [2]
   uint64_t *acc_empty = acc_full + 2;           // [2]
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+  uint64_t *pk_full = acc_empty + 2;             // [kPkStages]
+  uint64_t *pk_empty = pk_full + kPkStages;      // [kPkStages]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(pk_empty + kPkStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -107,8 +127,12 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     ptx::mbar_init(w_full, 1);
     ptx::mbar_init(a_ready, kEpiWarps);
     for (int i = 0; i < kStages; ++i) {
-      ptx::mbar_init(in_full + i, 1);
+      ptx::mbar_init(in_full + i, XBITS ? kExpWarps : 1);
       ptx::mbar_init(in_empty + i, 1);
+    }
+    for (int i = 0; i < kPkStages; ++i) {
+      ptx::mbar_init(pk_full + i, 1);
+      ptx::mbar_init(pk_empty + i, kExpWarps);
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(acc_full + i, 1);
@@ -132,12 +156,19 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
         const int b = item / a.strips, h0 = (item % a.strips) * TH;
         for (int t = 0; t < a.T; ++t, ++step) {
-          const uint32_t s = step % kStages, ph = (step / kStages) & 1;
-          ptx::mbar_wait(in_empty + s, ph ^ 1);
-          if (a.debug & 4) { ptx::mbar_arrive(in_full + s); continue; }     // timing bisection: no input loads
-          ptx::mbar_expect_tx(in_full + s, a.stage_tx_bytes);
-          ptx::tma_load_5d(stage_smem + s * kStageBytes, &tmap_x, in_full + s, 0, -1, h0 - 1,
-                           a.tb_swapped ? b : t, a.tb_swapped ? t : b);
+          if constexpr (XBITS) {
+            const uint32_t s = step % kPkStages, ph = (step / kPkStages) & 1;
+            ptx::mbar_wait(pk_empty + s, ph ^ 1);
+            ptx::mbar_expect_tx(pk_full + s, a.stage_tx_bytes);
+            ptx::tma_load_5d(pk_smem + s * kPkStageBytes, &tmap_x, pk_full + s, 0, -1, h0 - 1,
+                             a.tb_swapped ? b : t, a.tb_swapped ? t : b);
+          } else {
+            const uint32_t s = step % kStages, ph = (step / kStages) & 1;
+            ptx::mbar_wait(in_empty + s, ph ^ 1);
+            ptx::mbar_expect_tx(in_full + s, a.stage_tx_bytes);
+            ptx::tma_load_5d(stage_smem + s * kStageBytes, &tmap_x, in_full + s, 0, -1, h0 - 1,
+                             a.tb_swapped ? b : t, a.tb_swapped ? t : b);
+          }
         }
       }
     }
@@ -160,7 +191,7 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       uint32_t tap_off16[9];                       // (kh * P + kw) rows of 128 B, in 16-byte units
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) tap_off16[tap] = (uint32_t)(((tap / 3) * a.P + (tap % 3)) * 8);
-      const bool dense_path = ((nz_mask & 0xFFFFFFFFFull) == 0xFFFFFFFFFull) && !(a.debug & 1);
+      const bool dense_path = ((nz_mask & 0xFFFFFFFFFull) == 0xFFFFFFFFFull) && !UMMA_DBG(1);
       ptx::mbar_wait(w_full, 0);
       ptx::mbar_wait(a_ready, 0);
       ptx::tc_fence_after();
@@ -186,7 +217,7 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 if (tap < kTmemTaps)
                   ptx::mma_i8_ts(d_tmem, tmem_base + kACol0 + (tap * 4 + k) * 8, bd_tap + 2 * k, idesc, (tap | k) != 0);
                 else
-                  ptx::mma_i8(d_tmem, ad0 + ((tap - kTmemTaps) * kTapBytes + k * 32) / 16, bd_tap + 2 * k, idesc, 1);
+                  ptx::mma_i8(d_tmem, ad0 + ((tap - kTmemTaps) * kTapBytes + k * 32) / 16, bd_tap + 2 * k, idesc, (tap | k) != 0);
               }
             }
           } else {
@@ -194,7 +225,7 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             uint32_t accumulate = 0;
 #pragma unroll 1
             for (int sl = 0; sl < 36; ++sl) {
-              if (!((nz_mask >> sl) & 1) || (a.debug & 1)) continue;
+              if (!((nz_mask >> sl) & 1) || UMMA_DBG(1)) continue;
               const int tap = sl >> 2, k = sl & 3;
               const uint64_t bd = bd0 + tap_off16[tap] + 2 * k;
               if (tap < kTmemTaps)
@@ -206,6 +237,44 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           }
           ptx::mma_commit(in_empty + si);  // input stage reusable once these MMAs have read it
           ptx::mma_commit(acc_full + s);   // accumulator ready for the epilogue
+        }
+      }
+    }
+  } else if (warp >= kEpiWarps + 2) {
+    // ===================== expanders (XBITS): packed bits -> u8 operand rows =====================
+    if constexpr (XBITS) {
+      const int et = threadIdx.x - (kEpiWarps + 2) * 32;          // 0 .. 32 * kExpWarps - 1
+      const int ntask = 2 * a.box_rows;                           // (position, 64-channel half)
+      uint32_t step = 0;
+      for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
+        for (int t = 0; t < a.T; ++t, ++step) {
+          const uint32_t ps = step % kPkStages, pph = (step / kPkStages) & 1;
+          const uint32_t si = step % kStages, phi = (step / kStages) & 1;
+          ptx::mbar_wait(pk_full + ps, pph);
+          ptx::mbar_wait(in_empty + si, phi ^ 1);
+          const uint8_t *src = pk_smem + ps * kPkStageBytes;
+          uint8_t *dst = stage_smem + si * kStageBytes;
+          for (int task = et; task < ntask; task += 32 * kExpWarps) {
+            const int r = task >> 1, hf = task & 1;
+            const uint2 pkd = *reinterpret_cast<const uint2 *>(src + r * 16 + hf * 8);
+            uint8_t *row = dst + r * 128;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {                           // 16 channels = one 16-byte chunk
+              const uint32_t h16 = ((k & 2) ? pkd.y : pkd.x) >> ((k & 1) * 16);
+              uint4 o;
+              o.x = ((h16 & 0xFu) * 0x00204081u) & 0x01010101u;
+              o.y = (((h16 >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
+              o.z = (((h16 >> 8) & 0xFu) * 0x00204081u) & 0x01010101u;
+              o.w = (((h16 >> 12) & 0xFu) * 0x00204081u) & 0x01010101u;
+              *reinterpret_cast<uint4 *>(row + ((((hf << 2) | k) ^ (r & 7)) << 4)) = o;
+            }
+          }
+          ptx::fence_proxy_async();          // generic-proxy writes -> visible to the tensor core (async proxy)
+          __syncwarp();
+          if (lane == 0) {
+            ptx::mbar_arrive(in_full + si);
+            ptx::mbar_arrive(pk_empty + ps);
+          }
         }
       }
     }
@@ -264,7 +333,7 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(acc_empty + s);        // TMEM buffer free for step + 2
 
-        if (a.debug & 2) continue;
+        if (UMMA_DBG(2)) continue;
         if constexpr (FAST) {
           uint8_t *y0 = a.spikes + (int64_t)t * a.y_stride_t + (int64_t)b * a.y_stride_b + c;
           if constexpr (kPackedMath) {
@@ -292,6 +361,7 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           // scalar variant: I2FP conversion, exact for every int32 accumulator (any uint8 input)
           const LifParams<true> lifs{2.0f, 1.0f, 0.0f};
           int nspk = 0;
+          uint32_t mine = 0;          // y_bits: the 32-channel word of pooled position `lane` (16 per thread-step)
 #pragma unroll
           for (int pr = 0; pr < R / 2; ++pr) {
             uint8_t *yrow = y0 + ((int64_t)((h0 + r0 + 2 * pr) >> 1) * Wo + (w0 >> 1)) * kC;
@@ -305,8 +375,19 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 any |= sp;
                 if constexpr (COUNTS) nspk += sp ? 1 : 0;
               }
-              yrow[pc * kC] = any ? 1 : 0;
+              if (a.y_bits) {
+                const uint32_t bal = __ballot_sync(0xffffffffu, any);
+                if (lane == pr * (WC / 2) + pc) mine = bal;
+              } else {
+                yrow[pc * kC] = any ? 1 : 0;
+              }
             }
+          }
+          if (a.y_bits && lane < (R / 2) * (WC / 2)) {
+            const int prl = lane / (WC / 2), pcl = lane % (WC / 2);
+            uint8_t *yw = a.spikes + (int64_t)t * a.y_stride_t + (int64_t)b * a.y_stride_b +
+                          ((int64_t)((h0 + r0 + 2 * prl) >> 1) * Wo + (w0 >> 1) + pcl) * (kC / 8) + q * 4;
+            *reinterpret_cast<uint32_t *>(yw) = mine;
           }
           if constexpr (COUNTS) {
             if (nspk) atomicAdd(a.counts + ((int64_t)b * a.T + t) * kC + c, nspk);
@@ -376,23 +457,6 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 }
 
 // ---------------------------------------------------------------- host side ----
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void *p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  });
-  return fn;
-}
-
 int th_for(int W) { return W == 64 ? 2 : (W == 32 ? 4 : 8); }
 
 }  // namespace
@@ -409,7 +473,7 @@ bool umma_conv3x3_supported(const snnqp_block_params &p, const float *att) {
 int launch_conv3x3_umma(const snnqp_block_params &p, const uint8_t *x, const int8_t *wq, const float *scale,
                         const float *bias, uint8_t *spikes, float *u_final, int32_t *acc_dump, int32_t *counts,
                         cudaStream_t st) {
-  EncodeTiledFn encode = get_encode();
+  EncodeTiledFn encode = tmap_encoder();
   if (!encode) {
     set_error("cuTensorMapEncodeTiled not available from the driver");
     return SNNQP_ERR_CUDA;
@@ -421,41 +485,45 @@ int launch_conv3x3_umma(const snnqp_block_params &p, const uint8_t *x, const int
   const int N = (nflat + 15) / 16 * 16;
   if ((2 * P + 2 + N) * 128 > kStageBytes) return unsupported("tcgen05 conv: stage buffer too small for W=%d", p.W);
 
-  CUtensorMap tmx, tmw;
-  bool tb_swapped = false;
-  {
-    // a size-1 dimension may carry any stride: give it a sane one
-    const cuuint64_t img = (cuuint64_t)p.H * p.W * kC;
-    cuuint64_t st_t = p.T == 1 ? img : (cuuint64_t)p.x_stride_t;
-    cuuint64_t st_b = p.B == 1 ? img * p.T : (cuuint64_t)p.x_stride_b;
-    tb_swapped = st_t > st_b;          // keep the outer strides non-decreasing
-    cuuint64_t dims[5] = {(cuuint64_t)kC, (cuuint64_t)p.W, (cuuint64_t)p.H,
+  const bool xbits = p.x_format == SNNQP_SPIKES_BITS;
+  const int cbytes = xbits ? kC / 8 : kC;       // bytes per position of x
+  // a size-1 dimension may carry any stride: give it a sane one
+  const uint64_t img = (uint64_t)p.H * p.W * cbytes;
+  const uint64_t st_t = p.T == 1 ? img : (uint64_t)p.x_stride_t;
+  const uint64_t st_b = p.B == 1 ? img * p.T : (uint64_t)p.x_stride_b;
+  const bool tb_swapped = st_t > st_b;          // keep the outer strides non-decreasing
+  // tensor maps are cached per (pointer, geometry): encoding costs microseconds of host time per launch
+  const TmapKey kx{x, {p.T, p.B, p.H, p.W, xbits ? 1 : 0, 0}, {(int64_t)st_t, (int64_t)st_b}};
+  const CUtensorMap *tmx_p = tmap_cache_get(kx, [&](CUtensorMap *tm) {
+    cuuint64_t dims[5] = {(cuuint64_t)cbytes, (cuuint64_t)p.W, (cuuint64_t)p.H,
                           (cuuint64_t)(tb_swapped ? p.B : p.T), (cuuint64_t)(tb_swapped ? p.T : p.B)};
-    cuuint64_t strides[4] = {(cuuint64_t)kC, (cuuint64_t)p.W * kC, tb_swapped ? st_b : st_t, tb_swapped ? st_t : st_b};
-    cuuint32_t box[5] = {(cuuint32_t)kC, (cuuint32_t)P, (cuuint32_t)(TH + 2), 1, 1};
+    cuuint64_t strides[4] = {(cuuint64_t)cbytes, (cuuint64_t)p.W * cbytes, tb_swapped ? st_b : st_t, tb_swapped ? st_t : st_b};
+    cuuint32_t box[5] = {(cuuint32_t)cbytes, (cuuint32_t)P, (cuuint32_t)(TH + 2), 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = encode(&tmx, CU_TENSOR_MAP_DATA_TYPE_UINT8, 5, const_cast<uint8_t *>(x), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      set_error("cuTensorMapEncodeTiled(x) failed with CUresult %d (T=%d B=%d H=%d W=%d strides %lld/%lld)", (int)r,
-                p.T, p.B, p.H, p.W, (long long)p.x_stride_t, (long long)p.x_stride_b);
-      return SNNQP_ERR_CUDA;
-    }
+    return encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 5, const_cast<uint8_t *>(x), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, xbits ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  });
+  if (!tmx_p) {
+    set_error("cuTensorMapEncodeTiled(x) failed (T=%d B=%d H=%d W=%d strides %lld/%lld bits=%d)", p.T, p.B, p.H, p.W,
+              (long long)p.x_stride_t, (long long)p.x_stride_b, (int)xbits);
+    return SNNQP_ERR_CUDA;
   }
-  {
+  const TmapKey kw{wq, {9, kC, kC, 0, 0, 1}, {0, 0}};
+  const CUtensorMap *tmw_p = tmap_cache_get(kw, [&](CUtensorMap *tm) {
     cuuint64_t dims[2] = {(cuuint64_t)kC, (cuuint64_t)9 * kC};
     cuuint64_t strides[1] = {(cuuint64_t)kC};
     cuuint32_t box[2] = {(cuuint32_t)kC, (cuuint32_t)kC};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(&tmw, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t *>(wq), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      set_error("cuTensorMapEncodeTiled(w) failed with CUresult %d", (int)r);
-      return SNNQP_ERR_CUDA;
-    }
+    return encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t *>(wq), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  });
+  if (!tmw_p) {
+    set_error("cuTensorMapEncodeTiled(w) failed");
+    return SNNQP_ERR_CUDA;
   }
+  const CUtensorMap &tmx = *tmx_p, &tmw = *tmw_p;
 
   UmmaArgs a;
   a.T = p.T; a.B = p.B; a.H = p.H; a.W = p.W;
@@ -467,49 +535,43 @@ int launch_conv3x3_umma(const snnqp_block_params &p, const uint8_t *x, const int
   a.pool = p.pool;
   a.tb_swapped = tb_swapped ? 1 : 0;
   a.one = 1;
+  a.y_bits = p.y_format == SNNQP_SPIKES_BITS ? 1 : 0;
+  a.box_rows = (TH + 2) * P;
   a.base_off_mode = 0;   // the hardware applies the 128B swizzle on absolute smem address bits (measured)
+#ifdef SNNQP_C1_BISECT
   static const int dbg_env = getenv("SNNQP_UMMA_DEBUG") ? atoi(getenv("SNNQP_UMMA_DEBUG")) : 0;   // bisection switches (tools/)
   a.debug = dbg_env;
-  a.stage_tx_bytes = (uint32_t)((TH + 2) * P * kC);
+#else
+  a.debug = 0;
+#endif
+  a.stage_tx_bytes = (uint32_t)((TH + 2) * P * cbytes);
+  if (xbits && (int)a.stage_tx_bytes > kPkStageBytes) return unsupported("tcgen05 conv: packed stage too small for W=%d", p.W);
   a.scale = scale; a.bias = bias;
   a.slab_nz = reinterpret_cast<const uint8_t *>(wq) + kWBytes;   // blob tail written by snnqp_pack_conv3x3
   a.spikes = spikes; a.u_final = u_final; a.acc_dump = acc_dump; a.counts = counts; a.wq = wq;
 
   const int grid = a.total_items < sm_count() ? a.total_items : sm_count();
   const bool fast = p.tau == 2.0f && p.v_threshold == 1.0f && p.v_reset == 0.0f && p.pool && !u_final && !acc_dump;
-  constexpr int kSmemBytes = smem_bytes_for(7, 4);
-#define SNNQP_LAUNCH_UMMA(WV, FA, CO)                                                                          \
+  if (a.y_bits && !fast)
+    return unsupported("tcgen05 conv: bit-packed output needs the production variant (standard LIF constants, pool = 1, "
+                       "no u_final / acc_dump)");
+#define SNNQP_LAUNCH_UMMA(WV, FA, CO, XB)                                                                      \
   do {                                                                                                         \
-    SNNQP_CUDA(cudaFuncSetAttribute(k_conv3x3_umma<WV, FA, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                    kSmemBytes));                                                              \
-    k_conv3x3_umma<WV, FA, CO><<<grid, kThreads, kSmemBytes, st>>>(tmx, tmw, a);                               \
+    constexpr int kSm = smem_bytes_for(7, 4, XB);                                                              \
+    if (int rc = ensure_smem_attr<k_conv3x3_umma<WV, FA, CO, 7, 4, XB>>(kSm)) return rc;                       \
+    k_conv3x3_umma<WV, FA, CO, 7, 4, XB><<<grid, XB ? kThreadsX : kThreads, kSm, st>>>(tmx, tmw, a);           \
   } while (0)
-#define SNNQP_LAUNCH_UMMA_X(TT, ST)                                                                            \
-  do {                                                                                                         \
-    SNNQP_CUDA(cudaFuncSetAttribute(k_conv3x3_umma<64, true, false, TT, ST>,                                   \
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(TT, ST)));     \
-    k_conv3x3_umma<64, true, false, TT, ST><<<grid, kThreads, smem_bytes_for(TT, ST), st>>>(tmx, tmw, a);      \
-  } while (0)
-  // developer experiment (tools/time_conv2_variants.py): other TMEM / shared-memory splits of the W = 64 block
-  static const int split_env = getenv("SNNQP_C2_SPLIT") ? atoi(getenv("SNNQP_C2_SPLIT")) : 0;   // TT * 10 + ST
-  if (split_env && p.W == 64 && fast && !counts) {
-    switch (split_env) {
-      case 72: SNNQP_LAUNCH_UMMA_X(7, 2); break;
-      case 52: SNNQP_LAUNCH_UMMA_X(5, 2); break;
-      case 42: SNNQP_LAUNCH_UMMA_X(4, 2); break;
-      case 32: SNNQP_LAUNCH_UMMA_X(3, 2); break;
-      case 33: SNNQP_LAUNCH_UMMA_X(3, 3); break;
-      case 2: SNNQP_LAUNCH_UMMA_X(0, 2); break;
-      default: return invalid("SNNQP_C2_SPLIT: unknown split %d", split_env);
-    }
-    SNNQP_POST_LAUNCH("k_conv3x3_umma");
-    return SNNQP_OK;
-  }
 #define SNNQP_LAUNCH_UMMA_W(WV)                                             \
   do {                                                                      \
-    if (!fast) SNNQP_LAUNCH_UMMA(WV, false, false);                         \
-    else if (counts) SNNQP_LAUNCH_UMMA(WV, true, true);                     \
-    else SNNQP_LAUNCH_UMMA(WV, true, false);                                \
+    if (xbits) {                                                            \
+      if (!fast) SNNQP_LAUNCH_UMMA(WV, false, false, true);                 \
+      else if (counts) SNNQP_LAUNCH_UMMA(WV, true, true, true);             \
+      else SNNQP_LAUNCH_UMMA(WV, true, false, true);                        \
+    } else {                                                                \
+      if (!fast) SNNQP_LAUNCH_UMMA(WV, false, false, false);                \
+      else if (counts) SNNQP_LAUNCH_UMMA(WV, true, true, false);            \
+      else SNNQP_LAUNCH_UMMA(WV, true, false, false);                       \
+    }                                                                       \
   } while (0)
   if (p.W == 64) SNNQP_LAUNCH_UMMA_W(64);
   else if (p.W == 32) SNNQP_LAUNCH_UMMA_W(32);

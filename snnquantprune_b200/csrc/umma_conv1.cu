@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include "epilogue.cuh"
 #include "ptx.cuh"
+#include "tmap.cuh"
 
 namespace snnqp {
 
@@ -63,6 +64,7 @@ struct Conv1Args {
   int64_t y_stride_t, y_stride_b;
   float tau, v_th, v_reset;
   int pool, tb_swapped, debug;
+  int y_bits;                  // 1: emit bit-packed spikes (SNNQP_SPIKES_BITS), FAST variants only
   const int8_t *wq4;           // [4][cout][32] row-major
   const float *scale, *bias;
   uint8_t *spikes;
@@ -112,7 +114,10 @@ __device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {
 
 // FAST: standard LIF constants (tau 2, threshold 1, reset 0), pooled output, no
 // instrumentation outputs -- the production variant; !FAST handles everything else.
-template <bool FAST, int kEpiWarps>
+// LIFV (FAST only): 0 reference op order (FADD2 + FFMA2, FSET) | 1 single rounding fma(u, 0.5, v/2), FSET |
+// 2 single rounding, FFMA.SAT as the comparison (FMA pipe instead of the half-rate ALU pipe) | 3 single rounding,
+// FSET for quad positions 0-1 and FFMA.SAT for 2-3 (balances the two pipes).
+template <bool FAST, int kEpiWarps, int LIFV = 0>
 __global__ void __launch_bounds__(threads_for(kEpiWarps), 1)
 k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
   constexpr int kThreads = threads_for(kEpiWarps);
@@ -277,15 +282,25 @@ k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
       // spike words (two LOP3 per quad) and one shift.  The kernel is bound by issue slots, not by a pipe.
       constexpr int NP = NQ / 2;
       uint64_t u2[4][NP];
-      const uint64_t sc2 = pack2(sc, sc), bi2 = pack2(bi, bi), half2 = pack2(0.5f, 0.5f);
+      // LIFV >= 1: h = v / 2 = fma(acc, scale / 2, bias / 2) exactly (halving commutes with the rounding)
+      const float scv = LIFV == 0 ? sc : 0.5f * sc, biv = LIFV == 0 ? bi : 0.5f * bi;
+      const uint64_t sc2 = pack2(scv, scv), bi2 = pack2(biv, biv), half2 = pack2(0.5f, 0.5f);
       const uint32_t col0 = lane_addr + NQ * g;
+      // 1.0f if x >= 1 else 0.0f on the FMA pipe: sat(x * 2^24 + (1 - 2^24)) is exactly 1 for x >= 1 and exactly 0
+      // for x <= 1 - 2^-24 (the largest fp32 below 1): x * 2^24 is exact and the sum is rounded once.
+      auto sat_ge1 = [](float x) {
+        float d;
+        asm("fma.rn.sat.f32 %0, %1, 0f4B800000, 0fCB7FFFFF;" : "=f"(d) : "f"(x));
+        return d;
+      };
       // one LIF step of the neuron pair (quads 2p, 2p+1) at quad position j; returns the two spike words
-      auto lif_pair = [&](uint64_t &u, uint32_t a0, uint32_t a1, uint32_t &w0, uint32_t &w1) {
+      auto lif_pair = [&](uint64_t &u, uint32_t a0, uint32_t a1, uint32_t &w0, uint32_t &w1, int j) {
         const uint64_t v = fma2(pack2(__uint_as_float(a0), __uint_as_float(a1)), sc2, bi2);
-        const uint64_t un = fma2(sub2(v, u), half2, u);
+        const uint64_t un = LIFV == 0 ? fma2(sub2(v, u), half2, u) : fma2(u, half2, v);
         float ua, ub;
         unpack2(un, ua, ub);
-        const float s0 = fset_ge1(ua), s1 = fset_ge1(ub);
+        const bool use_sat = LIFV == 2 || (LIFV == 3 && j >= 2);
+        const float s0 = use_sat ? sat_ge1(ua) : fset_ge1(ua), s1 = use_sat ? sat_ge1(ub) : fset_ge1(ub);
         u = fma2(pack2(-s0, -s1), un, un);
         w0 = __float_as_uint(s0);
         w1 = __float_as_uint(s1);
@@ -299,7 +314,10 @@ k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
         for (int j = 0; j < 4; ++j)
 #pragma unroll
           for (int p = 0; p < NP; ++p) u2[j][p] = 0ull;
-        uint8_t *yrow = a.spikes + (int64_t)b * a.y_stride_b + c + ((int64_t)qh * Wo + qw0) * kC;
+        // u8 layout: one byte per (position, channel); bit layout: one 32-channel word per (position, lane quarter)
+        uint8_t *yrow = a.y_bits
+            ? a.spikes + (int64_t)b * a.y_stride_b + ((int64_t)qh * Wo + qw0 + lane) * (kC / 8) + q * 4
+            : a.spikes + (int64_t)b * a.y_stride_b + c + ((int64_t)qh * Wo + qw0) * kC;
         for (int t = 0; t < a.T; ++t, ++step, yrow += a.y_stride_t) {
           const uint32_t s = step % kAccStages, ph = (step / kAccStages) & 1;
           ptx::mbar_wait(acc_full + s, ph);
@@ -314,13 +332,30 @@ k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(acc_empty + s);
+          if (a.y_bits) {
+            // pooled spike of (quad, channel = lane) -> one ballot per quad = the 32-channel word of that position;
+            // lane i keeps the word of quad i and the warp stores NQ words with one instruction
+            uint32_t mine = 0;
 #pragma unroll
-          for (int p = 0; p < NP; ++p) {
-            uint32_t w[4][2];
+            for (int p = 0; p < NP; ++p) {
+              uint32_t w[4][2];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) lif_pair(u2[j][p], acc[j][2 * p], acc[j][2 * p + 1], w[j][0], w[j][1]);
-            yrow[(2 * p) * kC] = (uint8_t)(((w[0][0] | w[1][0]) | (w[2][0] | w[3][0])) >> 29);   // 0x3F800000 >> 29 == 1
-            yrow[(2 * p + 1) * kC] = (uint8_t)(((w[0][1] | w[1][1]) | (w[2][1] | w[3][1])) >> 29);
+              for (int j = 0; j < 4; ++j) lif_pair(u2[j][p], acc[j][2 * p], acc[j][2 * p + 1], w[j][0], w[j][1], j);
+              const uint32_t b0 = __ballot_sync(0xffffffffu, ((w[0][0] | w[1][0]) | (w[2][0] | w[3][0])) != 0u);
+              const uint32_t b1 = __ballot_sync(0xffffffffu, ((w[0][1] | w[1][1]) | (w[2][1] | w[3][1])) != 0u);
+              if (lane == 2 * p) mine = b0;
+              if (lane == 2 * p + 1) mine = b1;
+            }
+            if (lane < NQ) *reinterpret_cast<uint32_t *>(yrow) = mine;
+          } else {
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+              uint32_t w[4][2];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) lif_pair(u2[j][p], acc[j][2 * p], acc[j][2 * p + 1], w[j][0], w[j][1], j);
+              yrow[(2 * p) * kC] = (uint8_t)(((w[0][0] | w[1][0]) | (w[2][0] | w[3][0])) >> 29);   // 0x3F800000 >> 29 == 1
+              yrow[(2 * p + 1) * kC] = (uint8_t)(((w[0][1] | w[1][1]) | (w[2][1] | w[3][1])) >> 29);
+            }
           }
         }
       }
@@ -402,22 +437,6 @@ k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
   }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn get_encode1() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void *p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  });
-  return fn;
-}
-
 }  // namespace
 
 bool umma_conv1_supported(const snnqp_block_params &p, const float *att) {
@@ -430,29 +449,32 @@ bool umma_conv1_supported(const snnqp_block_params &p, const float *att) {
 // wq4: [4][128][32] quad-position weight matrices (snnqp_pack_conv1_quad)
 int launch_conv1_umma(const snnqp_block_params &p, const uint8_t *x, const int8_t *wq4, const float *scale,
                       const float *bias, uint8_t *spikes, float *u_final, int32_t *acc_dump, cudaStream_t st) {
-  EncodeTiledFn encode = get_encode1();
+  EncodeTiledFn encode = tmap_encoder();
   if (!encode) {
     set_error("cuTensorMapEncodeTiled not available from the driver");
     return SNNQP_ERR_CUDA;
   }
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(wq4) & 15))
     return invalid("tcgen05 conv1: x and wq must be 16-byte aligned");
-  CUtensorMap tmx;
   const cuuint64_t row = (cuuint64_t)p.W * 2, img = row * p.H;
-  cuuint64_t st_t = p.T == 1 ? img : (cuuint64_t)p.x_stride_t;
-  cuuint64_t st_b = p.B == 1 ? img * p.T : (cuuint64_t)p.x_stride_b;
+  const cuuint64_t st_t = p.T == 1 ? img : (cuuint64_t)p.x_stride_t;
+  const cuuint64_t st_b = p.B == 1 ? img * p.T : (cuuint64_t)p.x_stride_b;
   const bool swapped = st_t > st_b;
-  cuuint64_t dims[4] = {row, (cuuint64_t)p.H, (cuuint64_t)(swapped ? p.B : p.T), (cuuint64_t)(swapped ? p.T : p.B)};
-  cuuint64_t strides[3] = {row, swapped ? st_b : st_t, swapped ? st_t : st_b};
-  cuuint32_t box[4] = {(cuuint32_t)kStRowBytes, (cuuint32_t)kStRows, 1, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = encode(&tmx, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<uint8_t *>(x), dims, strides, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled(conv1 x) failed with CUresult %d", (int)r);
+  const TmapKey kx{x, {p.T, p.B, p.H, p.W, 0, 2}, {(int64_t)st_t, (int64_t)st_b}};
+  const CUtensorMap *tmx_p = tmap_cache_get(kx, [&](CUtensorMap *tm) {
+    cuuint64_t dims[4] = {row, (cuuint64_t)p.H, (cuuint64_t)(swapped ? p.B : p.T), (cuuint64_t)(swapped ? p.T : p.B)};
+    cuuint64_t strides[3] = {row, swapped ? st_b : st_t, swapped ? st_t : st_b};
+    cuuint32_t box[4] = {(cuuint32_t)kStRowBytes, (cuuint32_t)kStRows, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    return encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<uint8_t *>(x), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  });
+  if (!tmx_p) {
+    set_error("cuTensorMapEncodeTiled(conv1 x) failed");
     return SNNQP_ERR_CUDA;
   }
+  const CUtensorMap &tmx = *tmx_p;
   Conv1Args a;
   a.T = p.T; a.B = p.B; a.H = p.H; a.W = p.W;
   a.tiles_per_row = (p.W / 2) / kQuadsPerTile;
@@ -460,6 +482,7 @@ int launch_conv1_umma(const snnqp_block_params &p, const uint8_t *x, const int8_
   a.y_stride_t = p.y_stride_t; a.y_stride_b = p.y_stride_b;
   a.tau = p.tau; a.v_th = p.v_threshold; a.v_reset = p.v_reset;
   a.pool = p.pool; a.tb_swapped = swapped ? 1 : 0;
+  a.y_bits = p.y_format == SNNQP_SPIKES_BITS ? 1 : 0;
   static const int dbg_env = getenv("SNNQP_C1_DEBUG") ? atoi(getenv("SNNQP_C1_DEBUG")) : 0;   // bisection switches (tools/)
   a.debug = dbg_env;
   a.wq4 = wq4; a.scale = scale; a.bias = bias;
@@ -468,14 +491,28 @@ int launch_conv1_umma(const snnqp_block_params &p, const uint8_t *x, const int8_
   constexpr int kSmem = 4 * kWjBytes + kBStages * kBBytes + kStStages * kStBytes + 512 + 1024;
   const bool fast = p.tau == 2.0f && p.v_threshold == 1.0f && p.v_reset == 0.0f && p.pool && !u_final && !acc_dump;
   static const int ew_env = getenv("SNNQP_C1_EW") ? atoi(getenv("SNNQP_C1_EW")) : 16;
-  if (fast && ew_env == 16) {
-    SNNQP_CUDA(cudaFuncSetAttribute(k_conv1_umma<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    k_conv1_umma<true, 16><<<grid, threads_for(16), kSmem, st>>>(tmx, a);
+  if (a.y_bits && !fast)
+    return unsupported("tcgen05 conv1: bit-packed output needs the production variant (standard LIF constants, pool = 1, "
+                       "no u_final / acc_dump)");
+  if (p.x_format != SNNQP_SPIKES_U8) return unsupported("tcgen05 conv1: the input is event counts (SNNQP_SPIKES_U8)");
+  // SNNQP_LIF_FAST = variant 3 (see the template comment); lif_mode 101..103 select variant 1..3 (tests / tools)
+  const int lifv = p.lif_mode == SNNQP_LIF_FAST ? 3 : (p.lif_mode > 100 ? p.lif_mode - 100 : 0);
+#define SNNQP_LAUNCH_C1(LV)                                                                                        \
+  do {                                                                                                             \
+    if (int rc = ensure_smem_attr<k_conv1_umma<true, 16, LV>>(kSmem)) return rc;                                   \
+    k_conv1_umma<true, 16, LV><<<grid, threads_for(16), kSmem, st>>>(tmx, a);                                     \
+  } while (0)
+  if (fast && (ew_env == 16 || a.y_bits)) {
+    if (lifv == 0) SNNQP_LAUNCH_C1(0);
+    else if (lifv == 1) SNNQP_LAUNCH_C1(1);
+    else if (lifv == 2) SNNQP_LAUNCH_C1(2);
+    else SNNQP_LAUNCH_C1(3);
+#undef SNNQP_LAUNCH_C1
   } else if (fast) {
-    SNNQP_CUDA(cudaFuncSetAttribute(k_conv1_umma<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    if (int rc = ensure_smem_attr<k_conv1_umma<true, 8>>(kSmem)) return rc;
     k_conv1_umma<true, 8><<<grid, threads_for(8), kSmem, st>>>(tmx, a);
   } else {
-    SNNQP_CUDA(cudaFuncSetAttribute(k_conv1_umma<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    if (int rc = ensure_smem_attr<k_conv1_umma<false, 8>>(kSmem)) return rc;
     k_conv1_umma<false, 8><<<grid, threads_for(8), kSmem, st>>>(tmx, a);
   }
   SNNQP_POST_LAUNCH("k_conv1_umma");

@@ -31,12 +31,19 @@ from .pack import PackedCextNet
 class CextNetEngine:
   def __init__(self, packed: PackedCextNet, impl: int = _lib.IMPL_AUTO,
                tau: float = 2.0, v_threshold: float = 1.0, v_reset: float = 0.0,
-               chunk: int = 296, device="cuda"):
+               chunk: int = 296, device="cuda", lif_mode: int = _lib.LIF_EXACT,
+               packed_spikes: Optional[bool] = None):
+    """``packed_spikes``: conv1 -> conv2 -> conv3 -> conv4 exchange bit-packed spikes (SNNQP_SPIKES_BITS, 8x fewer
+    bytes; tcgen05 kernels only, the default unless impl == IMPL_SIMT).  ``lif_mode``: LIF_EXACT keeps the reference's
+    op order in every block; LIF_FAST lets conv1 (bound by its LIF epilogue) use the single-rounding form."""
     self.pk = packed
     self.impl = impl
+    self.lif_mode = lif_mode
+    self.packed_spikes = (impl != _lib.IMPL_SIMT) if packed_spikes is None else bool(packed_spikes)
     self.tau, self.v_th, self.v_reset = tau, v_threshold, v_reset
     self.chunk = chunk
     self.device = torch.device(device)
+    self.max_workspaces = 4
     self._ws: Dict[tuple, Dict[str, torch.Tensor]] = {}
     self._graphs: Dict[tuple, tuple] = {}
 
@@ -45,15 +52,21 @@ class CextNetEngine:
     key = (B, Bc)
     ws = self._ws.get(key)
     if ws is not None:
+      self._ws[key] = self._ws.pop(key)        # most recently used last
       return ws
+    while len(self._ws) >= self.max_workspaces:  # bounded: a serving loop over many batch sizes must not pin HBM
+      old = next(iter(self._ws))
+      self._graphs = {k: g for k, g in self._graphs.items() if k[1] != old[0]}
+      del self._ws[old]
     pk = self.pk
     T, H, C = pk.T, pk.H, pk.channels
     u8 = dict(device=self.device, dtype=torch.uint8)
     f32 = dict(device=self.device, dtype=torch.float32)
+    Cs = C // 8 if self.packed_spikes else C                     # bytes per position of s1 / s2 / s3
     ws = {
-        "s1": torch.empty((Bc, T, H // 2, H // 2, C), **u8),     # per chunk
-        "s2": torch.empty((Bc, T, H // 4, H // 4, C), **u8),     # per chunk
-        "s3": torch.empty((B, T, H // 8, H // 8, C), **u8),      # whole batch from here on
+        "s1": torch.empty((Bc, T, H // 2, H // 2, Cs), **u8),    # per chunk
+        "s2": torch.empty((Bc, T, H // 4, H // 4, Cs), **u8),    # per chunk
+        "s3": torch.empty((B, T, H // 8, H // 8, Cs), **u8),     # whole batch from here on
         "p4": torch.empty((B, T, H // 16, H // 16, C), **u8),
         "p5": torch.empty((B, T, H // 32, H // 32, C), **u8),
         "att4": torch.empty((B, T, C), **f32),
@@ -69,6 +82,10 @@ class CextNetEngine:
   def _bp(self, B, H, Cin, Cout, x: torch.Tensor, y: Optional[torch.Tensor],
           pool: int, att: Optional[torch.Tensor] = None, att_mod: int = 0) -> BlockParams:
     p = BlockParams()
+    # a spike tensor whose channel axis holds C / 8 bytes is bit-packed (SNNQP_SPIKES_BITS)
+    p.x_format = _lib.SPIKES_BITS if (Cin % 32 == 0 and x.dim() == 5 and x.shape[-1] * 8 == Cin) else _lib.SPIKES_U8
+    p.y_format = _lib.SPIKES_BITS if (y is not None and y.dim() == 5 and y.shape[-1] * 8 == Cout) else _lib.SPIKES_U8
+    p.lif_mode = self.lif_mode
     p.T, p.B, p.H, p.W, p.Cin, p.Cout = self.pk.T, B, H, H, Cin, Cout
     p.x_stride_b, p.x_stride_t = x.stride(0) * x.element_size(), x.stride(1) * x.element_size()
     if y is not None:
@@ -137,14 +154,34 @@ class CextNetEngine:
 
   def _head(self, frames_chunk, b0, n, ws, collect=None):
     H, C = self.pk.H, self.pk.channels
+    if collect is not None and self.packed_spikes:
+      # instrumented pass: the generic epilogues (un-pooled spikes, membranes, accumulators) emit SNNQP_SPIKES_U8
+      ws = self._u8_workspace(ws)
     s1, s2 = ws["s1"][:n], ws["s2"][:n]
     self._conv(0, frames_chunk, s1, n, H, 2, 1, collect=collect, key="conv1")
     self._conv(1, s1, s2, n, H // 2, C, 1, collect=collect, key="conv2")
     self._conv(2, s2, ws["s3"][b0:b0 + n], n, H // 4, C, 1, collect=collect, key="conv3")
 
+  def _u8_workspace(self, ws):
+    if "u8" not in ws:
+      C = self.pk.channels
+      u8 = dict(ws)
+      for k in ("s1", "s2", "s3"):
+        u8[k] = torch.empty(tuple(ws[k].shape[:-1]) + (C,), device=self.device, dtype=torch.uint8)
+      ws["u8"] = u8
+    return ws["u8"]
+
+  @staticmethod
+  def unpack_spikes(x: torch.Tensor) -> torch.Tensor:
+    """SNNQP_SPIKES_BITS (..., C/8) uint8 -> SNNQP_SPIKES_U8 (..., C) uint8 (bit c & 7 of byte c >> 3)."""
+    sh = torch.arange(8, device=x.device, dtype=torch.uint8)
+    return ((x.unsqueeze(-1) >> sh) & 1).reshape(tuple(x.shape[:-1]) + (x.shape[-1] * 8,))
+
   def _tail(self, B, ws, logits, collect=None):
     pk = self.pk
     H, C, T = pk.H, pk.channels, pk.T
+    if collect is not None and self.packed_spikes:
+      ws = self._u8_workspace(ws)
     if collect is None:
       # tail, fused: pooled spikes + spike counts straight from the conv epilogues
       ws["cnt4"].zero_(); ws["cnt5"].zero_()
@@ -185,13 +222,15 @@ class CextNetEngine:
       raise RuntimeError("densities() needs a forward first")
     ws = list(self._ws.values())[-1]
     T = self.pk.T
-    named = {"conv_1_inpt": ws["s1"], "conv_2_inpt": ws["s2"], "conv_3_inpt": ws["s3"], "conv_t_0_inpt": ws["p4"],
+    # the reference's sown names (models.py:128-173): conv_{0,1,2}_inpt for the first three blocks, conv_t_{0,1}_inpt
+    # for the two TCJA blocks (their inputs are s3 and the pooled block-4 spikes)
+    named = {"conv_1_inpt": ws["s1"], "conv_2_inpt": ws["s2"], "conv_t_0_inpt": ws["s3"], "conv_t_1_inpt": ws["p4"],
              "dense1_inpt": ws["p5"], "dense2_inpt": ws["d1"], "dense2_out": ws["d2"]}
     if frames is not None:
       named = dict(conv_0_inpt=frames, **named)
     out = {}
     for k, x in named.items():
-      d = density_stats(x, x.shape[0] * T)
+      d = density_stats(x, x.shape[0] * T, bits=self.packed_spikes and k in ("conv_1_inpt", "conv_2_inpt", "conv_t_0_inpt"))
       out[k] = {"min": float(d["min"]), "mean": float(d["mean"])}
     return out
 

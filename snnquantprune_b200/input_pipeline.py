@@ -69,16 +69,17 @@ def preprocess_data_number(addrs, times, config, wh, device="cuda") -> torch.Ten
   return fr[0]
 
 
-def density_stats(x: torch.Tensor, n_slices: int) -> dict:
+def density_stats(x: torch.Tensor, n_slices: int, bits: bool = False) -> dict:
   """The densities the reference sows per layer (examples/tcja/models.py:128-142): ``x`` is a
   contiguous uint8 device tensor whose leading ``n_slices`` = T*B (or B*T) slices are the
   (t, b) units.  Returns device tensors {"counts" int32 [n_slices], "min", "mean"} ('_min' is
-  the max density, as in the reference's naming)."""
+  the max density, as in the reference's naming).  ``bits``: ``x`` is bit-packed spikes
+  (SNNQP_SPIKES_BITS): set bits over 8 * bytes."""
   if x.dtype != torch.uint8 or not x.is_contiguous():
     raise ValueError("density_stats takes a contiguous uint8 tensor")
   slice_bytes = x.numel() // n_slices
   counts = torch.empty(n_slices, device=x.device, dtype=torch.int32)
-  _lib.check(_lib.lib().snnqp_slice_nonzeros(_lib.ptr(x), n_slices, slice_bytes, slice_bytes, _lib.ptr(counts),
-                                             _lib.stream()))
-  frac = counts.to(torch.float64) / float(slice_bytes)
+  fn = _lib.lib().snnqp_slice_popcount if bits else _lib.lib().snnqp_slice_nonzeros
+  _lib.check(fn(_lib.ptr(x), n_slices, slice_bytes, slice_bytes, _lib.ptr(counts), _lib.stream()))
+  frac = counts.to(torch.float64) / float(slice_bytes * (8 if bits else 1))
   return {"counts": counts, "min": frac.max(), "mean": frac.mean()}

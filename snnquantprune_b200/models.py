@@ -38,10 +38,34 @@ class CextNet:
 
   def __post_init__(self):
     self._engine: Optional[CextNetEngine] = None
-    self._packed_for: Optional[int] = None
+    self._packed_for = None
+
+  @staticmethod
+  def variables_digest(variables: Mapping[str, Any]) -> str:
+    """Content digest of everything the pack step reads (kernels, DuQ a/c, masks, BatchNorm affine and running
+    statistics).  The packed engine is cached on THIS, not on ``id(variables)``: ``import_torch_tcja`` and mask /
+    DuQ re-calibration update the tree in place, and a freed tree's id can be reused by a new dict."""
+    import hashlib
+    import numpy as np
+    h = hashlib.blake2b(digest_size=16)
+
+    def walk(prefix, node):
+      if isinstance(node, Mapping):
+        for k in sorted(node.keys()):
+          walk(prefix + "/" + str(k), node[k])
+      else:
+        a = node.detach().cpu().numpy() if isinstance(node, torch.Tensor) else np.asarray(node)
+        h.update(prefix.encode())
+        h.update(str(a.dtype).encode() + str(a.shape).encode())
+        h.update(np.ascontiguousarray(a).tobytes())
+    walk("", variables)
+    return h.hexdigest()
+
+  def invalidate(self) -> None:
+    self._engine, self._packed_for = None, None
 
   def engine(self, variables: Mapping[str, Any], H: int, device="cuda") -> CextNetEngine:
-    key = (id(variables), H)
+    key = (self.variables_digest(variables), H, str(device))
     if self._engine is None or self._packed_for != key:
       nd = self.config.neuron_dynamics()
       packed = pack_cextnet(variables, self.config.quant.bits, self.config.num_frames, H,

@@ -119,8 +119,11 @@ def test_engine_densities_match_oracle(cuda_lib):
   eng = CextNetEngine(pack_cextnet(v, bits, T, H, device="cuda"))
   c = {}
   eng.forward(fr, collect=c)
+  eng.forward(fr)                      # production pass: densities() reads ITS buffers (bit-packed s1 .. s3)
   d = eng.densities(fr)
-  for key, name in (("conv_0_inpt", None), ("conv_1_inpt", "s1"), ("conv_3_inpt", "s3"), ("dense2_inpt", "d1")):
+  # names as the reference sows them (examples/tcja/models.py:128-173): block 4's input is conv_t_0_inpt
+  for key, name in (("conv_0_inpt", None), ("conv_1_inpt", "s1"), ("conv_2_inpt", "s2"), ("conv_t_0_inpt", "s3"),
+                    ("conv_t_1_inpt", "p4"), ("dense2_inpt", "d1")):
     x = fr.cpu().numpy() if name is None else c[name].cpu().numpy()
     w = ref_events.sow_densities(np.swapaxes(x, 0, 1))             # (T, B, ...)
     assert abs(d[key]["min"] - w["min"]) < 1e-12 and abs(d[key]["mean"] - w["mean"]) < 1e-12, key

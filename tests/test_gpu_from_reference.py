@@ -87,7 +87,7 @@ def test_lif_bit_exact_vs_reference_multi_step_lif(cuda_lib, impl):
     p.y_stride_b, p.y_stride_t = y.stride(0), y.stride(1)
     p.tau, p.v_threshold, p.v_reset, p.pool, p.impl = 2.0, 1.0, 0.0, pool, impl
     u = torch.empty((B, H, W, C), device=DEV, dtype=torch.float32) if pool == 0 else None
-    _lib.check(cuda_lib.snnqp_spiking_conv3x3_fwd(p, P(x), P(blob), P(scale), P(bias), P(y), P(u), None, _lib.stream()))
+    _lib.check(cuda_lib.snnqp_spiking_conv3x3_fwd(p, P(x), None, P(blob), P(scale), P(bias), P(y), P(u), None, _lib.stream()))
     got = np.swapaxes(y.cpu().numpy(), 0, 1)
     if pool == 0:
       assert np.array_equal(got, ref_s)
@@ -151,6 +151,11 @@ def test_full_size_layerwise_vs_reference_cextnet(cuda_lib, tag):
   for i, (name, Hin, Cin) in enumerate((("conv1", H, 2), ("conv2", H // 2, C), ("conv3", H // 4, C))):
     y = conv_block_fast(i, name, x, Hin, Cin)
     flips[name] = reffix.compare_block(fx, name, np.swapaxes(y.cpu().numpy(), 0, 1))
+    # bit-packed spikes in and out (SNNQP_SPIKES_BITS: the production layout between conv1 .. conv4): same result
+    xb = x if Cin == 2 else dev(np.packbits(x.cpu().numpy(), axis=-1, bitorder="little"))
+    yb = torch.empty((B, T, Hin // 2, Hin // 2, C // 8), **u8)
+    eng._conv(i, xb, yb, B, Hin, Cin, 1)
+    assert np.array_equal(np.unpackbits(yb.cpu().numpy(), axis=-1, bitorder="little"), y.cpu().numpy()), name + " (bits)"
     c = {}
     yu = torch.empty((B, T, Hin, Hin, C), **u8)
     eng._conv(i, x, yu, B, Hin, Cin, 0, collect=c, key=name)
@@ -163,6 +168,9 @@ def test_full_size_layerwise_vs_reference_cextnet(cuda_lib, tag):
   p4 = conv_block_fast(3, "conv4", x, H // 8, C, counts=cnt)
   assert np.array_equal(p4.cpu().numpy(), ref_int.maxpool2_u8(s4.cpu().numpy()))
   assert np.array_equal(cnt.cpu().numpy(), s4.cpu().numpy().sum(axis=(2, 3), dtype=np.int32))
+  cnt2 = torch.zeros_like(cnt)                 # bit-packed input, u8 output + counts: what the production tail runs
+  p4b = conv_block_fast(3, "conv4", dev(np.packbits(x.cpu().numpy(), axis=-1, bitorder="little")), H // 8, C, counts=cnt2)
+  assert np.array_equal(p4b.cpu().numpy(), p4.cpu().numpy()) and np.array_equal(cnt2.cpu().numpy(), cnt.cpu().numpy())
   s4r = dev(bt(rs["conv4"]))
   cnt_r = dev(bt(fx["conv4_counts"]))
   att = torch.empty((B, T, C), device=DEV, dtype=torch.float32)

@@ -125,10 +125,12 @@ def test_fold_affine_bit_exact(cuda_lib):
 
 # ------------------------------------------------------- fused conv block ----
 def run_conv(lib, x_tb, wq, scale, bias, Cout, pool, impl, att=None, tau=2.0, batch_major=False, counts=None,
-             dumps=True):
+             dumps=True, x_bits=False, y_bits=False, lif_mode=0):
   """x_tb: numpy (T,B,H,W,Cin) u8.  Calls snnqp_spiking_conv3x3_fwd through the
   C-ABI; returns numpy (spikes (T,B,Ho,Wo,C), u (B,H,W,C), acc (T,B,H,W,C))."""
   T, B, H, W, Cin = x_tb.shape
+  if x_bits:
+    x_tb = np.packbits(x_tb, axis=-1, bitorder="little")          # SNNQP_SPIKES_BITS
   if batch_major:
     xs = dev(np.ascontiguousarray(np.swapaxes(x_tb, 0, 1)))
     xst, xsb = xs.stride(1), xs.stride(0)
@@ -136,7 +138,7 @@ def run_conv(lib, x_tb, wq, scale, bias, Cout, pool, impl, att=None, tau=2.0, ba
     xs = dev(x_tb)
     xst, xsb = xs.stride(0), xs.stride(1)
   Ho, Wo = (H // 2, W // 2) if pool else (H, W)
-  spikes = torch.full((T, B, Ho, Wo, Cout), 7, device=DEV, dtype=torch.uint8)
+  spikes = torch.full((T, B, Ho, Wo, Cout // 8 if y_bits else Cout), 7, device=DEV, dtype=torch.uint8)
   u = torch.empty((B, H, W, Cout), device=DEV, dtype=torch.float32)
   acc = torch.empty((T, B, H, W, Cout), device=DEV, dtype=torch.float32 if att is not None else torch.int32)
   p = BlockParams()
@@ -150,6 +152,7 @@ def run_conv(lib, x_tb, wq, scale, bias, Cout, pool, impl, att=None, tau=2.0, ba
   p.att_mod = Cin
   p.tau, p.v_threshold, p.v_reset = tau, 1.0, 0.0
   p.pool, p.impl = int(pool), impl
+  p.x_format, p.y_format, p.lif_mode = int(x_bits), int(y_bits), lif_mode
   ud, accd = (u, acc) if dumps else (None, None)      # no instrumentation outputs -> the production (FAST) variant
   if counts is None:
     _lib.check(lib.snnqp_spiking_conv3x3_fwd(p, P(xs), P(attd), P(wq), P(scale), P(bias), P(spikes), P(ud),
@@ -158,7 +161,10 @@ def run_conv(lib, x_tb, wq, scale, bias, Cout, pool, impl, att=None, tau=2.0, ba
     _lib.check(lib.snnqp_spiking_conv3x3_counts_fwd(p, P(xs), P(attd), P(wq), P(scale), P(bias), P(spikes), P(ud),
                                                     P(accd), P(counts), _lib.stream()))
   torch.cuda.synchronize()
-  return spikes.cpu().numpy(), u.cpu().numpy(), acc.cpu().numpy()
+  sp = spikes.cpu().numpy()
+  if y_bits:
+    sp = np.unpackbits(sp, axis=-1, bitorder="little")
+  return sp, u.cpu().numpy(), acc.cpu().numpy()
 
 
 def make_layer(rng, cin, cout, bits, p_prune):
@@ -192,6 +198,14 @@ def test_spiking_conv1_tcgen05_bit_exact(cuda_lib, oracle_lib, shape, bits, pool
     s_fast, _, _ = run_conv(cuda_lib, x, packed.wq, packed.scale, packed.bias, 128, pool, _lib.IMPL_TCGEN05,
                             batch_major=bm, dumps=False)
     assert np.array_equal(s_fast, s_ref)
+    if pool:
+      s_bits, _, _ = run_conv(cuda_lib, x, packed.wq, packed.scale, packed.bias, 128, pool, _lib.IMPL_TCGEN05,
+                              batch_major=bm, dumps=False, y_bits=True)
+      assert np.array_equal(s_bits, s_ref)                  # ballot-packed output, reference op-order LIF
+      for lm in (_lib.LIF_FAST, 101, 102, 103):             # single-rounding LIF variants: the flip budget
+        s_f, _, _ = run_conv(cuda_lib, x, packed.wq, packed.scale, packed.bias, 128, pool, _lib.IMPL_TCGEN05,
+                             batch_major=bm, dumps=False, y_bits=True, lif_mode=lm)
+        assert np.mean(s_f != s_ref) <= 1e-4, (lm, float(np.mean(s_f != s_ref)))
 
 
 @pytest.mark.parametrize("shape,bits,pool", [
@@ -249,6 +263,40 @@ def test_spiking_conv_binary_bit_exact(cuda_lib, oracle_lib, impl, shape, bits, 
   s_fast, _, _ = run_conv(cuda_lib, x, packed.wq, packed.scale, packed.bias, 128, pool, impl, batch_major=False,
                           dumps=False)
   assert np.array_equal(s_fast, s_ref)
+  if impl == _lib.IMPL_TCGEN05:
+    # bit-packed spikes (SNNQP_SPIKES_BITS): packed input through the expander warps with the instrumented epilogue,
+    # packed input and packed output with the production epilogue (pool only), both time/batch orders
+    s, u, acc = run_conv(cuda_lib, x, packed.wq, packed.scale, packed.bias, 128, pool, impl, batch_major=True, x_bits=True)
+    assert np.array_equal(acc, info["acc"]) and np.array_equal(s, s_ref) and np.array_equal(u, info["u"])
+    if pool:
+      for bm in (True, False):
+        cnt.zero_()
+        s_fast, _, _ = run_conv(cuda_lib, x, packed.wq, packed.scale, packed.bias, 128, pool, impl, batch_major=bm,
+                                counts=cnt if bm else None, dumps=False, x_bits=True, y_bits=True)
+        assert np.array_equal(s_fast, s_ref)
+      assert np.array_equal(cnt.cpu().numpy(), info["spikes"].sum(axis=(2, 3), dtype=np.int32).transpose(1, 0, 2))
+  else:
+    with pytest.raises(_lib.SnnqpError):          # no silent fallback: the SIMT kernels speak SNNQP_SPIKES_U8 only
+      run_conv(cuda_lib, x, packed.wq, packed.scale, packed.bias, 128, pool, impl, dumps=False, x_bits=True)
+
+
+@pytest.mark.parametrize("cin,cout", [(128, 96), (2, 96), (64, 64)])
+def test_spiking_conv_simt_cout_not_dividing_block(cuda_lib, oracle_lib, cin, cout):
+  """Cout = 96 does not divide the SIMT block (512 / 256 threads): the spare threads must not redo a neighbour
+  block's quad -- spike counts (TCJA input) would be double-counted."""
+  T, B, H, W, bits = 3, 2, 16, 16, 8
+  rng = np.random.default_rng(cin + cout)
+  lay, q, bn, stt = make_layer(rng, cin, cout, bits, 0.4)
+  x = (rng.uniform(size=(T, B, H, W, cin)) < 0.3).astype(np.uint8)
+  packed = pk_mod.pack_conv3x3(lay, bits, DEV, bn, stt)
+  scale, bias = ref_int.fold_affine(lay["DuQ_0"]["c"], bits, bn, stt, cout)
+  s_ref, info = ref_int.spiking_conv3x3(x, q, scale, bias, pool=True, want=True)
+  cnt = torch.zeros((B, T, cout), device=DEV, dtype=torch.int32) if cin != 2 else None
+  s, u, acc = run_conv(cuda_lib, x, packed.wq, packed.scale, packed.bias, cout, True, _lib.IMPL_SIMT, batch_major=True,
+                       counts=cnt)
+  assert np.array_equal(acc, info["acc"]) and np.array_equal(s, s_ref) and np.array_equal(u, info["u"])
+  if cnt is not None:
+    assert np.array_equal(cnt.cpu().numpy(), info["spikes"].sum(axis=(2, 3), dtype=np.int32).transpose(1, 0, 2))
 
 
 @pytest.mark.parametrize("impl", impls())
@@ -358,7 +406,10 @@ def run_dense(lib, x, wq, scale, bias, N, att=None, att_mod=0, impl=_lib.IMPL_SI
   _lib.check(lib.snnqp_spiking_dense_fwd(p, P(xs), P(attd), P(wq), P(scale), P(bias), P(spikes), P(u), P(acc),
                                          _lib.stream()))
   torch.cuda.synchronize()
-  return spikes.cpu().numpy(), u.cpu().numpy(), acc.cpu().numpy()
+  sp = spikes.cpu().numpy()
+  if y_bits:
+    sp = np.unpackbits(sp, axis=-1, bitorder="little")
+  return sp, u.cpu().numpy(), acc.cpu().numpy()
 
 
 @pytest.mark.parametrize("impl", impls())

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
   for name in declared:
     assert hasattr(lib, name), f"libsnnqp.so does not export {name}"
   assert declared == set(_lib.SIGNATURES.keys())
-  assert lib.snnqp_abi_version() == 1
+  assert lib.snnqp_abi_version() == _lib.ABI_VERSION == int(re.search(r"#define SNNQP_ABI_VERSION (\d+)", header).group(1))
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
@@ -206,3 +206,18 @@ def test_host_chunk_schedule_covers_batch_and_respects_cap():
       assert sched[0][1] == min(16, cap, B)
       body = [n for _, n in sched[:-1]]
       assert body == sorted(body)
+
+
+def test_cextnet_engine_cache_key_follows_content():
+  """The facade caches its packed engine on a content digest: an in-place edit of the variable tree (what
+  import_torch_tcja / re-calibration do) must change the key, an untouched tree must not."""
+  from snnquantprune_b200 import synthetic
+  from snnquantprune_b200.models import CextNet
+  v = synthetic.make_variables(bits=8, prune_percentage=0.5, T=3, H=32, seed=2)
+  d0 = CextNet.variables_digest(v)
+  assert CextNet.variables_digest(v) == d0
+  v["params"]["QuantConv_1"]["prune_0"]["mask"][0, 0, 0, 0] = 1 - v["params"]["QuantConv_1"]["prune_0"]["mask"][0, 0, 0, 0]
+  d1 = CextNet.variables_digest(v)
+  assert d1 != d0
+  v["batch_stats"]["BatchNorm_2"]["var"][5] *= 1.5
+  assert CextNet.variables_digest(v) != d1
