@@ -97,19 +97,36 @@ class ClockSampler:
 
 
 def cpu_reference_samples_per_s(bits, prune, T, H, sample_B, reps, threads):
-  """The oracle's fp32 restatement of the reference graph on the host cores."""
+  """The oracle's fp32 restatement of the reference graph on the host cores (configs[0],
+  batch 16, one warm-up pass on one sample, median of >= 5 passes)."""
   import torch
   from oracle import ref_snn
   from snnquantprune_b200 import synthetic
   torch.set_num_threads(threads)
   v = synthetic.make_variables(bits=bits, prune_percentage=prune, T=T, H=H, seed=1)
   fr = synthetic.make_frames(sample_B, T, H, H, seed=0)
+  ref_snn.cextnet_forward(v, fr[:1], bits)
   times = []
   for _ in range(reps):
     t0 = time.perf_counter()
     ref_snn.cextnet_forward(v, fr, bits)
     times.append(time.perf_counter() - t0)
   return sample_B / statistics.median(times), times
+
+
+def parity_of_timed_batch(v, bits, H, frames_np, gpu_logits_np, T):
+  """Checker (outside every timed region): the first samples of the batch that was just timed, through the
+  integer-path oracle (oracle/ref_net.py, pinned to the executed reference by tests/test_from_reference_cpu.py),
+  against the logits the timed engine produced for them."""
+  import numpy as np
+  from oracle import build as obuild, ref_net
+  obuild.build()
+  lo = ref_net.forward(ref_net.pack_network(v, bits, H), frames_np)
+  d = np.abs(lo - gpu_logits_np)
+  return {"samples": int(frames_np.shape[0]), "logits_max_abs_diff": float(d.max()),
+          "logit_quantum": 1.0 / (T * 10), "argmax_agree": bool(np.array_equal(lo.argmax(-1), gpu_logits_np.argmax(-1))),
+          "bit_identical_logits": bool(np.array_equal(lo, gpu_logits_np)),
+          "oracle": "oracle/ref_net.py integer path (reference-order LIF); engine runs LIF_FAST in conv1"}
 
 
 def run_reference(args):
@@ -131,7 +148,7 @@ def run_reference(args):
     ref_snn.cextnet_forward(v, fr[:1], args.bits)
     t1 = time.perf_counter() - t0                     # seconds per sample, last warm-up pass
   # bounded sample: the K timed steps together take about two and a half minutes at most, whatever K is
-  sample_B = max(1, min(sample_B, int(150.0 / (max(1, args.steps) * max(t1, 1e-3)))))
+  sample_B = max(1, min(sample_B, int(270.0 / (max(1, args.steps) * max(t1, 1e-3)))))
   fr = fr[:sample_B]
   t0 = time.perf_counter()
   for _ in range(args.steps):
@@ -223,23 +240,36 @@ def run_ours(args):
 
   # ---- end to end: pinned host frames -> H2D -> forward -> logits D2H ------
   # the public host-memory call: chunked H2D on a copy stream overlapped with compute, logits copied back
+  # Inputs travel in the zero-suppressed frame format (include/snnqp.h snnqp_expand_frames_zsf: cell bitmap + the
+  # non-zero counts, encoded once by the data-loader side before the timed region, like the pinned dense frames
+  # were); the dense-frame call is timed beside it.
+  from snnquantprune_b200.input_pipeline import zsf_encode
   host_logits = torch.empty((B, packed.num_classes), dtype=torch.float32).pin_memory()
   eng_e2e = CextNetEngine(packed, impl=impl, chunk=args.e2e_chunk, device=dev)
   e2e_steps = max(1, min(args.steps, args.e2e_steps))
-  for _ in range(2):
-    eng_e2e.forward_host(host_frames, host_logits)
-  torch.cuda.synchronize(); D.barrier()
-  e0.record()
-  for _ in range(e2e_steps):
-    eng_e2e.forward_host(host_frames, host_logits)
-  e1.record()
-  torch.cuda.synchronize(); D.barrier()
-  t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-  D.reduce_max(t)
-  e2e_value = B * ws * e2e_steps / (float(t.item()) / 1e3)
+  zb = zsf_encode(host_frames.numpy())
+
+  def time_e2e(call):
+    for _ in range(2):
+      call()
+    torch.cuda.synchronize(); D.barrier()
+    e0.record()
+    for _ in range(e2e_steps):
+      call()
+    e1.record()
+    torch.cuda.synchronize(); D.barrier()
+    tt = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    D.reduce_max(tt)
+    return B * ws * e2e_steps / (float(tt.item()) / 1e3)
+
+  e2e_value = time_e2e(lambda: eng_e2e.forward_host_zsf(zb, host_logits))
+  torch.cuda.synchronize()
+  e2e_logits_ok = bool(torch.equal(host_logits, logits.cpu()))       # same logits as the device-resident pass
+  e2e_dense = time_e2e(lambda: eng_e2e.forward_host(host_frames, host_logits))
 
   # ---- dominant kernel (conv2 block), timed live with CUDA events ----------
   roof = dominant_kernel_roofline(eng, frames, args, dev)
+  roof_kernels = per_kernel_rooflines(eng, frames, ms_max / args.steps, roof["peak"])
   # per-layer input densities of the synthetic run (a dead network would make the throughput meaningless)
   eng.forward(frames)
   rates = {k: round(v["mean"], 4) for k, v in eng.densities(frames).items()}
@@ -253,13 +283,15 @@ def run_ours(args):
 
   if rank == 0:
     pk = peaks()
-    cpu = None
+    cpu = parity = None
     if ws == 1 and not args.no_cpu_baseline:
       threads = os.cpu_count() or 1
-      val, times = cpu_reference_samples_per_s(args.bits, args.prune, T, H, args.cpu_batch, 2, threads)
+      val, times = cpu_reference_samples_per_s(args.bits, args.prune, T, H, args.cpu_batch, args.cpu_passes, threads)
       cpu = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-             "sample": f"{args.cpu_batch} samples of the same workload, median of 2 passes, oracle fp32 restatement "
-                       f"of the reference graph (torch-CPU contractions); the JAX reference cannot run in this image"}
+             "sample": f"BASELINE.json configs[0]: {args.cpu_batch} samples of the same workload, 1 warm-up, median of "
+                       f"{args.cpu_passes} passes, oracle fp32 restatement of the reference graph (torch-CPU "
+                       f"contractions); the JAX reference cannot run in this image"}
+      parity = parity_of_timed_batch(v, args.bits, H, host_frames[:2].numpy(), logits[:2].cpu().numpy(), T)
     net_tops = value * GOP_PER_SAMPLE_T20 / 1e3 / ws          # dense-equivalent int8 TOP/s per GPU
     line = {
         "metric": METRIC.replace("T=20", f"T={args.T}"), "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
@@ -269,12 +301,18 @@ def run_ours(args):
         "config": dict(workload_config(args, B, ws),
                        arithmetic="int8 weights x u8 spikes/counts -> int32 accumulate (tcgen05 kind::i8; conv1 as exact "
                                   "kind::f16), fp32 dequant + BatchNorm + LIF epilogue"),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_frames.numel()) * ws,
-                "d2h_bytes_per_step": int(host_logits.numel() * 4) * ws, "steps": e2e_steps},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(zb.nbytes) * ws,
+                "d2h_bytes_per_step": int(host_logits.numel() * 4) * ws, "steps": e2e_steps,
+                "input_format": f"zero-suppressed frames (bitmap + {zb.value_bits}-bit non-zero counts), "
+                                f"{zb.nbytes / B / 1e3:.0f} KB/sample instead of {host_frames.numel() / B / 1e3:.0f} KB dense uint8",
+                "logits_equal_device_resident_pass": e2e_logits_ok,
+                "dense_uint8_frames": {"value": e2e_dense, "unit": UNIT, "h2d_bytes_per_step": int(host_frames.numel()) * ws}},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roof,
+        "roofline_kernels": roof_kernels,
         "cpu_baseline": cpu,
+        "parity": parity,
         "network_roofline": {"bound": "tensor", "achieved": value * GOP_PER_SAMPLE_T20 / 1e3, "unit": "TOP/s",
                              "achieved_per_gpu": net_tops, "gop_per_sample": GOP_PER_SAMPLE_T20,
                              "peak_nominal_int8": 4500.0, "frac_nominal": net_tops / 4500.0,
@@ -326,7 +364,7 @@ def dominant_kernel_roofline(eng, frames, args, dev):
   ops = CONV2_GOP_PER_SAMPLE * 1e9 * Bc * (pk.T / 20.0) * (pk.H / 128.0) ** 2
   pkp = peaks()
   traffic = None
-  tpath = os.path.join(ROOT, "profiles", "r1_conv2_traffic.json")
+  tpath = os.path.join(ROOT, "profiles", "r2_conv2_traffic.json")
   if os.path.exists(tpath):
     tj = json.load(open(tpath))          # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
     if tj.get("samples_per_launch") == Bc and tj.get("T") == pk.T:
@@ -349,6 +387,53 @@ def dominant_kernel_roofline(eng, frames, args, dev):
           "peak_nominal_int8": 4500.0, "frac_of_nominal_int8": achieved / 4500.0}
 
 
+def per_kernel_rooflines(eng, frames, ms_step, int8_peak_tops):
+  """One entry per fused launch with >= 10 % of the step: CUDA-event time of the launch on one head chunk, its share of
+  the step, and BOTH rooflines -- dense-equivalent int8 OP/s against the measured tensor-pipe ceiling and algorithmic
+  HBM bytes (u8 frames in, bit-packed pooled spikes out / in) against the measured copy bandwidth."""
+  import torch
+  pk = eng.pk
+  B = frames.shape[0]
+  n = min(eng.chunk, B)
+  ws = eng._workspace(B, n)
+  T, H, C = pk.T, pk.H, pk.channels
+  hbm = peaks()["hbm"]
+  scale = (T / 20.0) * (H / 128.0) ** 2
+  px = lambda h: T * h * h * C / 8 / 1e6 if eng.packed_spikes else T * h * h * C / 1e6       # MB / sample
+  specs = [
+      ("conv1 fused block (k_conv1_umma: 128x128x2 -> 128, LIF, pool)", lambda: eng._conv(0, frames[:n], ws["s1"][:n], n, H, 2, 1),
+       2 * 0.755 * scale, T * H * H * 2 / 1e6 + px(H // 2), n),
+      ("conv2 fused block (k_conv3x3_umma<64>)", lambda: eng._conv(1, ws["s1"][:n], ws["s2"][:n], n, H // 2, C, 1),
+       2 * 12.080 * scale, px(H // 2) + px(H // 4), n),
+      ("conv3 fused block (k_conv3x3_umma<32>)", lambda: eng._conv(2, ws["s2"][:n], ws["s3"][:n], n, H // 4, C, 1),
+       2 * 3.020 * scale, px(H // 4) + px(H // 8), n),
+  ]
+  out = []
+  chunks_per_step = B / n
+  for name, fn, gop, mb, units in specs:
+    for _ in range(2):
+      fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(5):
+      fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    share = ms * chunks_per_step / ms_step
+    if share < 0.10:
+      continue
+    tops = gop * units / ms / 1e3
+    gbs = mb * units / ms
+    out.append({"kernel": name, "ms_per_launch": ms, "samples_per_launch": units, "share_of_step": share,
+                "tensor": {"achieved": tops, "peak": int8_peak_tops, "unit": "TOP/s", "frac": tops / int8_peak_tops},
+                "hbm": {"achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                        "algorithmic_mb_per_sample": mb},
+                "bound": "tensor" if tops / int8_peak_tops > gbs / hbm else "issue slots of the LIF epilogue (neither roofline)"})
+  return out
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
@@ -364,10 +449,11 @@ def main():
   ap.add_argument("--prune", type=float, default=0.5)
   ap.add_argument("--T", type=int, default=20)
   ap.add_argument("--H", type=int, default=128)
-  ap.add_argument("--e2e-steps", type=int, default=5)
+  ap.add_argument("--e2e-steps", type=int, default=20)
+  ap.add_argument("--cpu-passes", type=int, default=5)
   ap.add_argument("--e2e-chunk", type=int, default=296, help="largest H2D / head chunk of the end-to-end path (chunks grow from 16)")
-  ap.add_argument("--cpu-batch", type=int, default=8)
-  ap.add_argument("--ref-batch", type=int, default=8)
+  ap.add_argument("--cpu-batch", type=int, default=16)
+  ap.add_argument("--ref-batch", type=int, default=16)
   ap.add_argument("--no-cpu-baseline", action="store_true")
   args = ap.parse_args()
   if args.warmup < 3 and args.impl == "ours":

@@ -258,6 +258,25 @@ int snnqp_events_to_frames(const int32_t *addrs, const int64_t *offsets, int B,
 int snnqp_slice_nonzeros(const uint8_t *x, int n_slices, int64_t slice_bytes,
                          int64_t stride_slice, int32_t *counts, void *stream);
 
+/* Zero-suppressed frames: the host -> device wire format of the end-to-end path.
+ * The reference hands the model dense (T, H, W, 2) event-count frames
+ * (examples/input_pipeline.py:142-219, train_inpt_spikingjelly.py:300-305); they
+ * are mostly zeros, and at 8 GPUs the dense uint8 frames saturate the host ->
+ * device links.  Cells are the flattened [B][T][H][W][2] frame bytes in blocks
+ * of 1024 (n_cells % 1024 == 0):
+ *   bitmap    uint32 [n_blocks][32]: bit (i & 31) of word (i >> 5) <=> cell i != 0
+ *   block_off uint32 [n_blocks + 1]: index (in values, counted in elements)
+ *             of each block's first value, minus value_base -- a batch is encoded
+ *             once and any sample range of it can be shipped and expanded
+ *   values    the non-zero counts in cell order, value_bits = 4 (low nibble
+ *             first; every count <= 15) or 8 bits each
+ * Writes frames uint8 [n_blocks * 1024] (16-byte aligned).  Encoder / decoder on
+ * the host: snnquantprune_b200/input_pipeline.py (zsf_encode), oracle/ref_events.py. */
+int snnqp_expand_frames_zsf(const uint32_t *bitmap, const uint32_t *block_off,
+                            const uint8_t *values, uint32_t value_base,
+                            int64_t n_blocks, int value_bits, uint8_t *frames,
+                            void *stream);
+
 /* Same for a bit-packed spike tensor (SNNQP_SPIKES_BITS): counts[s] = set bits
  * of slice s -- the same numerator, one eighth of the bytes. */
 int snnqp_slice_popcount(const uint8_t *x, int n_slices, int64_t slice_bytes,

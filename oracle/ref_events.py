@@ -49,3 +49,20 @@ def sow_densities(x: np.ndarray):
   nz = (x.reshape(T, B, -1) != 0).sum(-1)
   frac = nz / np.prod(x.shape[2:])
   return {"counts": nz.astype(np.int64), "min": float(frac.max()), "mean": float(frac.mean())}
+
+
+def zsf_decode(bitmap_u32: np.ndarray, block_off: np.ndarray, values: np.ndarray, value_base: int, n_blocks: int,
+               value_bits: int) -> np.ndarray:
+  """Decoder of the zero-suppressed frame wire format (include/snnqp.h, snnqp_expand_frames_zsf), plain numpy:
+  returns the n_blocks * 1024 dense uint8 cells."""
+  bits = np.unpackbits(np.ascontiguousarray(bitmap_u32[:n_blocks * 32]).view(np.uint8), bitorder="little").astype(bool)
+  if value_bits == 4:
+    v = np.stack([values & 0xF, values >> 4], -1).reshape(-1)
+  else:
+    v = values
+  out = np.zeros(n_blocks * 1024, np.uint8)
+  for k in range(n_blocks):
+    m = bits[k * 1024:(k + 1) * 1024]
+    start = int(block_off[k]) - int(value_base)
+    out[k * 1024:(k + 1) * 1024][m] = v[start:start + int(m.sum())]
+  return out

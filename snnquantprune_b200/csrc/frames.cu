@@ -176,3 +176,71 @@ extern "C" int snnqp_slice_popcount(const uint8_t *x, int n_slices, int64_t slic
                                     int32_t *counts, void *stream_) {
   return slice_count(x, n_slices, slice_bytes, stride_slice, counts, true, stream_);
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Zero-suppressed frames (the host -> device wire format of the end-to-end path).  DVS event-count frames are
+// mostly zeros (the reference's frames, input_pipeline.py:142-219, are dense (T, H, W, 2) arrays; the synthetic
+// workload has ~14 % non-zero cells), and at 8 GPUs the dense uint8 frames saturate the box's host -> device
+// bandwidth.  Wire format per batch of cells (flattened [B][T][H][W][2], 1024 cells per block):
+//   bitmap      uint32 [n_blocks][32]   bit (i & 31) of word i >> 5 set <=> cell i is non-zero
+//   block_off   uint32 [n_blocks + 1]   running count of non-zero cells before each block
+//   values      the non-zero counts in cell order: 4 bits each (value_bits == 4: low nibble first; every count
+//               <= 15) or 8 bits each (value_bits == 8)
+// k_expand_zsf: one warp per block; lane l owns word l (32 cells): warp prefix sum of the popcounts locates its
+// values; the 32 expanded bytes leave as two 128-bit stores.  Bytes moved: ~(1/8 + density * value_bits / 8) per
+// cell in, 1 per cell out.
+namespace snnqp {
+namespace {
+template <int VB>
+__global__ void __launch_bounds__(256)
+k_expand_zsf(const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ block_off,
+             const uint8_t *__restrict__ values, uint32_t value_base, int64_t n_blocks, uint8_t *__restrict__ frames) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t blk = warp; blk < n_blocks; blk += nwarps) {
+    const uint32_t bits = __ldg(bitmap + blk * 32 + lane);
+    const int n = __popc(bits);
+    int incl = n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
+    }
+    uint32_t pos = __ldg(block_off + blk) - value_base + (uint32_t)(incl - n);       // index of this lane's first value
+    uint32_t out[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t rem = bits;
+    while (rem) {
+      const int i = __ffs(rem) - 1;
+      rem &= rem - 1;
+      uint32_t v;
+      if (VB == 4) v = (__ldg(values + (pos >> 1)) >> ((pos & 1) * 4)) & 0xFu;
+      else v = __ldg(values + pos);
+      ++pos;
+      out[i >> 2] |= v << ((i & 3) * 8);
+    }
+    uint4 *dst = reinterpret_cast<uint4 *>(frames + (blk * 32 + lane) * 32);
+    dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
+    dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
+  }
+}
+}  // namespace
+}  // namespace snnqp
+
+extern "C" int snnqp_expand_frames_zsf(const uint32_t *bitmap, const uint32_t *block_off, const uint8_t *values,
+                                       uint32_t value_base, int64_t n_blocks, int value_bits, uint8_t *frames,
+                                       void *stream_) {
+  using namespace snnqp;
+  if (int r = require_device()) return r;
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  if (!bitmap || !block_off || !values || !frames) return invalid("snnqp_expand_frames_zsf: null pointer");
+  if (n_blocks <= 0) return invalid("snnqp_expand_frames_zsf: n_blocks must be > 0");
+  if (value_bits != 4 && value_bits != 8) return invalid("snnqp_expand_frames_zsf: value_bits=%d (4 or 8)", value_bits);
+  if (reinterpret_cast<uintptr_t>(frames) & 15) return invalid("snnqp_expand_frames_zsf: frames must be 16-byte aligned");
+  int64_t g = (n_blocks + 7) / 8;                      // 8 warps per CTA
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (g > cap) g = cap;
+  if (value_bits == 4) k_expand_zsf<4><<<(int)g, 256, 0, st>>>(bitmap, block_off, values, value_base, n_blocks, frames);
+  else k_expand_zsf<8><<<(int)g, 256, 0, st>>>(bitmap, block_off, values, value_base, n_blocks, frames);
+  SNNQP_POST_LAUNCH("k_expand_zsf");
+  return SNNQP_OK;
+}

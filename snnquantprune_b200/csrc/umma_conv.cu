@@ -46,7 +46,7 @@ constexpr int kEpiWarps = 8;
 constexpr int kThreads = (kEpiWarps + 2) * 32;  // + TMA warp + MMA warp
 // Bit-packed input (SNNQP_SPIKES_BITS): TMA stages the packed tile (16 B per position), two expander warps turn
 // bits into the u8 K-major 128B-swizzled MMA operand (3 integer ops per 4 bytes: nibble * 0x00204081 & 0x01010101).
-constexpr int kExpWarps = 2;
+constexpr int kExpWarps = 4;
 constexpr int kThreadsX = kThreads + kExpWarps * 32;
 constexpr int kPkStages = 4, kPkStageBytes = 4352;   // >= (TH+2) * (W+2) * 16 B for every config, 128-aligned
 constexpr int kTmemCols = 512;
@@ -61,10 +61,6 @@ constexpr int kACol0 = 2 * kAccStride;          // first TMEM column of the resi
 constexpr int smem_bytes_for(int tt, int st, bool xbits = false) {
   return (9 - tt) * kTapBytes + st * kStageBytes + (xbits ? kPkStages * kPkStageBytes : 0) + 1024 /*barriers*/ + 1024 /*align slack*/;
 }
-// Fast-epilogue flavour.  The packed f32x2 form converts with the magic-number trick, exact only for
-// |acc| < 2^22 ({0,1} inputs); the scalar form (I2FP) is exact for any uint8 input.  This kernel is bound by
-// the tensor pipe (97 % active), so the always-exact scalar form is the default.
-constexpr bool kPackedMath = false;
 
 struct UmmaArgs {
   int T, B, H, W;
@@ -308,70 +304,51 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(a_ready);
     }
-    float u[R][WC];                 // generic variant
-    uint64_t u2[R][WC / 2];         // FAST variant: packed pairs (columns 2p, 2p+1)
-    const Lif2Consts k2(sc, bi, a.one);
+    float u[R][WC];                 // membranes: in registers for all T steps of a strip
     uint32_t step = 0;
     for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
       const int b = item / a.strips, h0 = (item % a.strips) * TH;
 #pragma unroll
       for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int j = 0; j < WC; ++j) { u[r][j] = 0.0f; u2[r][j >> 1] = 0ull; }   // zero carry (spiking_learning.py:464-472)
+        for (int j = 0; j < WC; ++j) u[r][j] = 0.0f;   // zero carry (spiking_learning.py:464-472)
       for (int t = 0; t < a.T; ++t, ++step) {
         const uint32_t s = step & 1, ph = (step >> 1) & 1;
         ptx::mbar_wait(acc_full + s, ph);
         ptx::tc_fence_after();
-        uint32_t acc[R][WC];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const uint32_t taddr = lane_addr + s * kAccStride + (r0 + r) * a.P + w0;
-          if constexpr (WC == 32) { SNNQP_TMEM_LD_X32(taddr, acc[r]); } else { SNNQP_TMEM_LD_X16(taddr, acc[r]); }
-        }
-        ptx::tc_wait_ld();
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(acc_empty + s);        // TMEM buffer free for step + 2
-
-        if (UMMA_DBG(2)) continue;
         if constexpr (FAST) {
-          uint8_t *y0 = a.spikes + (int64_t)t * a.y_stride_t + (int64_t)b * a.y_stride_b + c;
-          if constexpr (kPackedMath) {
-            // packed f32x2 variant (magic-number conversion: exact only for |acc| < 2^22, i.e. {0,1} inputs)
-            uint64_t cnt2 = 0ull;
-#pragma unroll
-            for (int pr = 0; pr < R / 2; ++pr) {
-              uint8_t *yrow = y0 + ((int64_t)((h0 + r0 + 2 * pr) >> 1) * Wo + (w0 >> 1)) * kC;
-#pragma unroll
-              for (int pc = 0; pc < WC / 2; ++pc) {
-                const uint64_t st = lif2_std(u2[2 * pr][pc], acc[2 * pr][2 * pc], acc[2 * pr][2 * pc + 1], k2);
-                const uint64_t sb = lif2_std(u2[2 * pr + 1][pc], acc[2 * pr + 1][2 * pc], acc[2 * pr + 1][2 * pc + 1], k2);
-                yrow[pc * kC] = pool2x2(st, sb);
-                if constexpr (COUNTS) cnt2 = add2(cnt2, add2(st, sb));
-              }
-            }
-            if constexpr (COUNTS) {
-              float ca, cb;
-              unpack2(cnt2, ca, cb);
-              const int nspk = (int)(ca + cb);
-              if (nspk) atomicAdd(a.counts + ((int64_t)b * a.T + t) * kC + c, nspk);
-            }
-            continue;
-          }
-          // scalar variant: I2FP conversion, exact for every int32 accumulator (any uint8 input)
+          // Production epilogue, register-lean: the accumulators arrive in chunks of 2 rows x 16 columns (8 pooled
+          // outputs), so a thread holds its 64 membranes + 32 accumulators (the TMEM buffer is released after the
+          // last chunk is in registers; the MMAs of the next step run on the other buffer meanwhile).
+          // I2FP conversion: exact for every int32 accumulator (any uint8 input).
+          constexpr int CW = 16, NCC = WC / CW, NCH = (R / 2) * NCC;
           const LifParams<true> lifs{2.0f, 1.0f, 0.0f};
           int nspk = 0;
           uint32_t mine = 0;          // y_bits: the 32-channel word of pooled position `lane` (16 per thread-step)
+          uint8_t *y0 = a.spikes + (int64_t)t * a.y_stride_t + (int64_t)b * a.y_stride_b + c;
 #pragma unroll
-          for (int pr = 0; pr < R / 2; ++pr) {
+          for (int ch = 0; ch < NCH; ++ch) {
+            const int pr = ch / NCC, cc = ch % NCC;
+            uint32_t a0[CW], a1[CW];
+            const uint32_t taddr = lane_addr + s * kAccStride + (r0 + 2 * pr) * a.P + w0 + cc * CW;
+            SNNQP_TMEM_LD_X16(taddr, a0);
+            SNNQP_TMEM_LD_X16(taddr + a.P, a1);
+            ptx::tc_wait_ld();
+            if (ch == NCH - 1) {
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive(acc_empty + s);        // TMEM buffer free for step + 2
+            }
             uint8_t *yrow = y0 + ((int64_t)((h0 + r0 + 2 * pr) >> 1) * Wo + (w0 >> 1)) * kC;
 #pragma unroll
-            for (int pc = 0; pc < WC / 2; ++pc) {
+            for (int p8 = 0; p8 < CW / 2; ++p8) {
+              const int pc = cc * (CW / 2) + p8;
               bool any = false;
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const int r = 2 * pr + (e >> 1), j = 2 * pc + (e & 1);
-                const bool sp = lifs.step(u[r][j], __fmaf_rn((float)(int32_t)acc[r][j], sc, bi));
+                const uint32_t av = (e >> 1) ? a1[2 * p8 + (e & 1)] : a0[2 * p8 + (e & 1)];
+                const bool sp = lifs.step(u[r][j], __fmaf_rn((float)(int32_t)av, sc, bi));
                 any |= sp;
                 if constexpr (COUNTS) nspk += sp ? 1 : 0;
               }
@@ -394,6 +371,18 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           }
           continue;
         }
+        uint32_t acc[R][WC];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const uint32_t taddr = lane_addr + s * kAccStride + (r0 + r) * a.P + w0;
+          if constexpr (WC == 32) { SNNQP_TMEM_LD_X32(taddr, acc[r]); } else { SNNQP_TMEM_LD_X16(taddr, acc[r]); }
+        }
+        ptx::tc_wait_ld();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(acc_empty + s);        // TMEM buffer free for step + 2
+
+        if (UMMA_DBG(2)) continue;
         const LifParams<false> lif{a.tau, a.v_th, a.v_reset};
         uint32_t m[R];
 #pragma unroll

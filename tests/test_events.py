@@ -93,7 +93,7 @@ def test_events_feed_the_hot_path(cuda_lib):
   fr, _ = ip.events_to_frames(addrs.cuda(), off.cuda(), T, H)
   want = ref_events.batch_to_frames(samples, T, H, 1, saturate_u8=True)[0]
   v = synthetic.make_variables(bits=bits, prune_percentage=0.5, T=T, H=H, seed=1)
-  eng = CextNetEngine(pack_cextnet(v, bits, T, H, device="cuda"))
+  eng = CextNetEngine(pack_cextnet(v, bits, T, H, device="cuda"), lif_mode=0)
   assert np.array_equal(eng.forward(fr).cpu().numpy(), eng.forward(torch.as_tensor(want).cuda()).cpu().numpy())
 
 
@@ -116,7 +116,7 @@ def test_engine_densities_match_oracle(cuda_lib):
   bits, T, H, B = 8, 4, 32, 3
   v = synthetic.make_variables(bits=bits, prune_percentage=0.5, T=T, H=H, seed=1)
   fr = torch.as_tensor(synthetic.make_frames(B, T, H, H, seed=2)).cuda()
-  eng = CextNetEngine(pack_cextnet(v, bits, T, H, device="cuda"))
+  eng = CextNetEngine(pack_cextnet(v, bits, T, H, device="cuda"), lif_mode=0)
   c = {}
   eng.forward(fr, collect=c)
   eng.forward(fr)                      # production pass: densities() reads ITS buffers (bit-packed s1 .. s3)
@@ -171,3 +171,73 @@ def test_events_and_density_kernels_match_golden_fixture(cuda_lib):
       assert int(sat.item()) == int(z[f"n_saturated_rs{rs}"])
     d = ip.density_stats(f8, f8.shape[0] * T)
     assert np.array_equal(d["counts"].cpu().numpy().reshape(f8.shape[0], T).T, z[f"density_counts_rs{rs}"])
+
+
+# ---- zero-suppressed frames: the host -> device wire format of the end-to-end path --------------------------------
+def _zsf_cases():
+  from snnquantprune_b200 import synthetic
+  fr = synthetic.make_frames(6, 4, 32, 32, seed=3)
+  fr[1] = 0                                   # an empty sample
+  fr[2] = np.maximum(fr[2], 1)                # every cell non-zero
+  fr[3, 0, 0, 0, 0] = 15                      # the largest 4-bit count
+  yield "nibble", fr
+  fr = fr.copy()
+  fr[4, 1, 2, 3, 1] = 255                     # forces 8-bit values
+  yield "byte", fr
+  yield "all_zero", np.zeros((2, 4, 32, 32, 2), np.uint8)
+
+
+def test_zsf_round_trip_cpu():
+  """encode (product, numpy) -> decode (oracle, numpy) is the identity for every sample range."""
+  from snnquantprune_b200 import input_pipeline as ip2
+  for name, fr in _zsf_cases():
+    z = ip2.zsf_encode(fr)
+    assert z.value_bits == (8 if name == "byte" else 4)
+    B = fr.shape[0]
+    for b0, b1 in ((0, B), (1, B - 1), (B - 1, B), (0, 1)):
+      if b1 <= b0:
+        continue
+      bm, bo, v, base, nb = z.chunk(b0, b1)
+      d = ref_events.zsf_decode(bm.numpy().view(np.uint32), bo.numpy().view(np.uint32), v.numpy(), base, nb, z.value_bits)
+      assert np.array_equal(d, fr[b0:b1].reshape(-1)), (name, b0, b1)
+    assert z.nbytes < fr.nbytes or name == "nibble" or name == "byte"
+  with pytest.raises(ValueError):
+    ip2.zsf_encode(np.zeros((1, 3, 5, 5, 2), np.uint8))       # cells not a multiple of 1024
+
+
+@pytest.mark.gpu
+def test_zsf_expand_kernel_bit_exact(cuda_lib):
+  from snnquantprune_b200 import input_pipeline as ip2
+  for name, fr in _zsf_cases():
+    z = ip2.zsf_encode(fr)
+    B = fr.shape[0]
+    for b0, b1 in ((0, B), (1, B - 1), (B - 1, B)):
+      if b1 <= b0:
+        continue
+      bm, bo, v, base, nb = z.chunk(b0, b1)
+      out = torch.full((nb * 1024,), 7, device="cuda", dtype=torch.uint8)
+      vd = torch.cat([v, torch.zeros(16, dtype=torch.uint8)]).cuda()
+      ip2.zsf_expand(bm.cuda(), bo.cuda(), vd, base, nb, z.value_bits, out)
+      assert np.array_equal(out.cpu().numpy(), fr[b0:b1].reshape(-1)), (name, b0, b1)
+
+
+@pytest.mark.gpu
+def test_forward_host_zsf_equals_device_forward(cuda_lib):
+  """The end-to-end host call in the zero-suppressed wire format gives exactly the logits of the device-resident
+  forward and of the dense-frame host call (reference geometry, ragged chunk schedule)."""
+  from snnquantprune_b200 import CextNetEngine, pack_cextnet, synthetic
+  from snnquantprune_b200 import input_pipeline as ip2
+  bits, T, H, B = 8, 20, 128, 45
+  v = synthetic.make_variables(bits=bits, prune_percentage=0.5, T=T, H=H, seed=1)
+  fr = synthetic.make_frames(B, T, H, H, seed=5)
+  eng = CextNetEngine(pack_cextnet(v, bits, T, H, device="cuda"), chunk=37)
+  want = eng.forward(torch.as_tensor(fr).cuda()).cpu()
+  z = ip2.zsf_encode(fr)
+  assert z.nbytes < 0.3 * fr.nbytes
+  host_out = torch.empty_like(want).pin_memory()
+  eng.forward_host_zsf(z, host_out)
+  torch.cuda.synchronize()
+  assert torch.equal(host_out, want)
+  eng.forward_host(torch.as_tensor(fr).pin_memory(), host_out)
+  torch.cuda.synchronize()
+  assert torch.equal(host_out, want)

@@ -96,10 +96,10 @@ def test_lif_bit_exact_vs_reference_multi_step_lif(cuda_lib, impl):
       assert np.array_equal(got, ref_int.maxpool2_u8(ref_s))
 
 
-def _engine(v, m, chunk=16, impl=_lib.IMPL_AUTO):
+def _engine(v, m, chunk=16, impl=_lib.IMPL_AUTO, lif_mode=_lib.LIF_EXACT):
   from snnquantprune_b200 import CextNetEngine, pack_cextnet
   return CextNetEngine(pack_cextnet(v, m["bits"], m["T"], m["H"], num_classes=m["num_classes"], device=DEV),
-                       impl=impl, chunk=chunk)
+                       impl=impl, chunk=chunk, lif_mode=lif_mode)
 
 
 @pytest.mark.parametrize("tag", ["T4_H32_b8_p50", "T3_H32_b4_p80", "T3_H32_b2_p90", "T10_H32_b8_p50_c10"])
@@ -192,10 +192,12 @@ def test_full_size_layerwise_vs_reference_cextnet(cuda_lib, tag):
     eng._dense(lay, B, xin, a, y, c, name)
     flips[name] = reffix.compare_block(fx, name, np.swapaxes(y.cpu().numpy(), 0, 1), u_final=c[name + "_u"].cpu().numpy())
   assert sum(flips.values()) <= 8, flips
-  # free-running production forward: logits within the flip-derived tolerance of the reference's
-  logits = eng.forward(dev(fr)).cpu().numpy()
-  assert np.max(np.abs(logits - fx["logits"])) <= 0.02, (logits, fx["logits"])
-  assert np.array_equal(np.argmax(logits, -1), np.argmax(fx["logits"], -1))
+  # free-running production forward (bit-packed spikes; reference-order LIF, then the engine's default LIF_FAST):
+  # logits within the flip-derived tolerance of the reference's
+  for lm in (_lib.LIF_EXACT, _lib.LIF_FAST):
+    logits = _engine(v, m, chunk=296, lif_mode=lm).forward(dev(fr)).cpu().numpy()
+    assert np.max(np.abs(logits - fx["logits"])) <= 0.02, (lm, logits, fx["logits"])
+    assert np.array_equal(np.argmax(logits, -1), np.argmax(fx["logits"], -1))
 
 
 def test_production_shape_chunk_296(cuda_lib, oracle_lib):
@@ -211,6 +213,8 @@ def test_production_shape_chunk_296(cuda_lib, oracle_lib):
   l296 = _engine(v, m, chunk=296).forward(frd).cpu().numpy()
   l16 = _engine(v, m, chunk=16).forward(frd).cpu().numpy()
   assert np.array_equal(l296, l16)
+  lfast = _engine(v, m, chunk=296, lif_mode=_lib.LIF_FAST).forward(frd).cpu().numpy()     # the bench's configuration
+  assert np.mean(np.abs(lfast - l296) > 1e-6) <= 0.01 and np.max(np.abs(lfast - l296)) <= 0.02
   pkd = ref_net.pack_network(v, bits, H)
   idx = [0, 295, 299]
   lo = ref_net.forward(pkd, fr[idx])
