@@ -183,6 +183,18 @@ int snnqp_spiking_conv3x3_counts_fwd(const snnqp_block_params *p, const uint8_t 
                                      uint8_t *spikes, float *u_final, void *acc_dump,
                                      int32_t *spike_counts, void *stream);
 
+/* Plain quantized contraction behind the QuantDense facade (flax_qdense.py:
+ * 59-106, lax.dot_general :87-89) and the 1-D k = 4 'SAME' QuantConv facade
+ * (flax_qconv.py:131-168 as TCJA uses it, examples/tcja/models.py:52-59,77-84;
+ * rows = im2col of the (1, 2)-padded input):
+ *   y[m][n] = (sum_k x[m][k] * q[k][n]) * scale[0]
+ * x: fp32 or uint8 [M][K] contiguous; q_kn: int8 levels in the reference's own
+ * (in, out) / (k, in, out) layout (snnqp_pack_levels); scale: device scalar
+ * c / L (snnqp_fold_affine, n = 1).  Not a hot-path call. */
+int snnqp_qlinear_fwd(const void *x, int x_is_u8, const int8_t *q_kn,
+                      const float *scale, int64_t M, int K, int N, float *y,
+                      void *stream);
+
 /* SpikingBlock(QuantDense, multi_step_LIF), no norm (models.py:200-246).
  *   x uint8 [T,B,Cin] via strides; wq int8 [Cout][k_pad] with k_pad = Cin
  *   rounded up to 16; att as above with index k % att_mod. */

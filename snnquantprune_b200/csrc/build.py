@@ -12,11 +12,13 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 OUT = os.path.join(os.path.dirname(HERE), "libsnnqp.so")
-SOURCES = ["runtime.cu", "pack.cu", "simt.cu", "umma_conv.cu", "umma_conv1.cu", "umma_att.cu", "diag.cu", "frames.cu", "api.cu"]
+SOURCES = ["runtime.cu", "pack.cu", "simt.cu", "umma_conv.cu", "umma_conv1.cu", "umma_att.cu", "diag.cu", "frames.cu", "plain.cu", "api.cu", "xla_ffi_shim.cc"]
 HEADERS = ["common.cuh", "ptx.cuh", "tmap.cuh", "epilogue.cuh", os.path.join(ROOT, "include", "snnqp.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+# XLA FFI handlers (xla_ffi_shim.cc) compile for real where jaxlib's headers are: SNNQP_XLA_INCLUDE=<dir holding xla/ffi/api/ffi.h>
+XLA_INC = ["-I", os.environ["SNNQP_XLA_INCLUDE"]] if os.environ.get("SNNQP_XLA_INCLUDE") else []
 if os.environ.get("SNNQP_BISECT"):          # debug-only bisection switches inside the hot loops (tools/)
   FLAGS.append("-DSNNQP_C1_BISECT")
 
@@ -39,9 +41,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
   os.makedirs(build_dir, exist_ok=True)
   procs = []
   for s in SOURCES:
-    o = os.path.join(build_dir, s.replace(".cu", ".o"))
+    o = os.path.join(build_dir, s.replace(".cu", ".o").replace(".cc", ".o"))
     objs.append(o)
-    cmd = [NVCC, *FLAGS, "-I", os.path.join(ROOT, "include"), "-I", HERE, "-c",
+    cmd = [NVCC, *FLAGS, "-I", os.path.join(ROOT, "include"), "-I", HERE, *XLA_INC, "-c",
            os.path.join(HERE, s), "-o", o]
     procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
   logs = []

@@ -219,3 +219,37 @@ def test_production_shape_chunk_296(cuda_lib, oracle_lib):
   idx = [0, 295, 299]
   lo = ref_net.forward(pkd, fr[idx])
   assert np.max(np.abs(l296[idx] - lo)) <= 0.02 and np.array_equal(np.argmax(l296[idx], -1), np.argmax(lo, -1))
+
+
+def _layer_params(tag):
+  from snnquantprune_b200.synthetic import StableRNG
+  srng = StableRNG(int(OPS[f"{tag}_seed"]))
+  kshape = tuple(int(v) for v in OPS[f"{tag}_kshape"])
+  k = (srng.standard_normal(kshape) * 0.3).astype(F32)
+  m = (srng.uniform(0, 1, kshape) > 0.5).astype(F32)
+  assert reffix.sha(k, m) == str(OPS[f"{tag}_ksha"])
+  return {"params": {"kernel": k, "DuQ_0": {"a": OPS[f"{tag}_a"], "c": OPS[f"{tag}_c"]}, "prune_0": {"mask": m}}}
+
+
+def test_layer_facades_vs_reference_quantconv_quantdense(cuda_lib):
+  """The drop-in layer facades called on their own (same constructor fields as the reference's modules) against the
+  outputs of the reference's QuantConv.__call__ (3x3 pad 1 and 1-D k = 4 'SAME') and QuantDense.__call__."""
+  from snnquantprune_b200 import QuantConv, QuantDense, QuantConfig
+  cfg = QuantConfig(bits=4, g_scale=0.0, prune_percentage=0.5)
+  y = QuantConv(features=128, kernel_size=(3, 3), padding=((1, 1), (1, 1)), use_bias=False, config=cfg, bits=4,
+                g_scale=0.0).apply(_layer_params("qconv3x3"), dev(OPS["qconv3x3_x"]))
+  ref = OPS["qconv3x3_y"]
+  assert np.max(np.abs(y.cpu().numpy() - ref)) <= 2e-6 * np.max(np.abs(ref))
+  y = QuantConv(features=5, kernel_size=[4], padding="SAME", use_bias=False, config=cfg, bits=4,
+                g_scale=0.0).apply(_layer_params("qconv1d"), dev(OPS["qconv1d_x"]))
+  assert y.shape == OPS["qconv1d_y"].shape and np.max(np.abs(y.cpu().numpy() - OPS["qconv1d_y"])) <= 1e-6
+  y1 = QuantConv(features=5, kernel_size=4, padding="SAME", use_bias=False, config=cfg, bits=4,
+                 g_scale=0.0).apply(_layer_params("qconv1d"), dev(OPS["qconv1d_x"][0]))       # single input (W, Cin)
+  assert np.array_equal(y1.cpu().numpy(), y[0].cpu().numpy())
+  for x in (dev(OPS["qdense_x"]), dev(OPS["qdense_x"].astype(F32))):
+    y = QuantDense(110, use_bias=False, config=cfg, bits=4, g_scale=0.0).apply(_layer_params("qdense"), x)
+    ref = OPS["qdense_y"]
+    assert np.max(np.abs(y.cpu().numpy() - ref)) <= 2e-6 * np.max(np.abs(ref))
+  with pytest.raises(NotImplementedError):
+    QuantConv(features=5, kernel_size=[4], padding="VALID", use_bias=False, config=cfg).apply(
+        _layer_params("qconv1d"), dev(OPS["qconv1d_x"]))

@@ -221,3 +221,26 @@ def test_cextnet_engine_cache_key_follows_content():
   assert d1 != d0
   v["batch_stats"]["BatchNorm_2"]["var"][5] *= 1.5
   assert CextNet.variables_digest(v) != d1
+
+
+def test_xla_ffi_shim_type_checks_against_mock_header(tmp_path):
+  """csrc/xla_ffi_shim.cc (the XLA custom-call handlers a maintainer registers from JAX) is compiled
+  against tests/mock_xla -- a stand-in for jaxlib's ffi.h whose Bind() DSL static_asserts that every handler is
+  callable with exactly the bound context / argument / result / attribute types.  A deliberately wrong binding must
+  fail, so the check is not vacuous.  (In the product build the TU is part of libsnnqp.so, empty without the header.)"""
+  import shutil
+  import subprocess
+  gxx = shutil.which("g++")
+  assert gxx
+  inc = ["-I", os.path.join(ROOT, "tests", "mock_xla"), "-I", os.path.join(ROOT, "include"), "-I", "/usr/local/cuda/include"]
+  src = os.path.join(ROOT, "snnquantprune_b200", "csrc", "xla_ffi_shim.cc")
+  r = subprocess.run([gxx, "-std=c++17", "-fsyntax-only", *inc, src], capture_output=True, text=True)
+  assert r.returncode == 0, r.stderr
+  text = open(src).read()
+  handlers = re.findall(r"XLA_FFI_DEFINE_HANDLER_SYMBOL\((\w+),", text)
+  assert len(handlers) >= 13 and {"SnnqpSpikingConvCounts", "SnnqpSpikingConvAtt", "SnnqpSpikingDenseAtt",
+                                  "SnnqpPackConv", "SnnqpPackMatrix", "SnnqpFoldAffine"} <= set(handlers)
+  bad = tmp_path / "bad.cc"
+  bad.write_text(text.replace('.Attr<int32_t>("group"));', '.Attr<float>("group").Attr<int32_t>("extra"));'))
+  r = subprocess.run([gxx, "-std=c++17", "-fsyntax-only", *inc, str(bad)], capture_output=True, text=True)
+  assert r.returncode != 0 and "not callable with the types bound" in r.stderr
