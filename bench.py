@@ -424,7 +424,7 @@ def per_kernel_rooflines(eng, frames, ms_step, int8_peak_tops):
     share = ms * chunks_per_step / ms_step
     if share < 0.10:
       continue
-    tops = gop * units / ms / 1e3
+    tops = gop * units / ms                      # GOP / ms = TOP/s
     gbs = mb * units / ms
     out.append({"kernel": name, "ms_per_launch": ms, "samples_per_launch": units, "share_of_step": share,
                 "tensor": {"achieved": tops, "peak": int8_peak_tops, "unit": "TOP/s", "frac": tops / int8_peak_tops},

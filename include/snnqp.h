@@ -239,6 +239,13 @@ int snnqp_vote_fwd(const uint8_t *spikes, int T, int B, int N, int group,
 int snnqp_eval_metrics(const float *logits, const int32_t *labels, int B,
                        int classes, float *out2, void *stream);
 
+/* Spike-tile skip statistics of the bit-packed tcgen05 3x3 block: an input
+ * box (one strip x one timestep) whose bits are all zero issues no MMAs (its
+ * accumulators are taken as 0; the LIF update still runs).  *skipped / *total =
+ * boxes skipped / seen by all launches since the last reset (device-wide
+ * counters; the call synchronises with the device). */
+int snnqp_tile_skip_stats(int64_t *skipped, int64_t *total, int reset);
+
 /* Number of kernels this library has launched on this thread since the last
  * call with reset != 0 (bench.py's gpu_launches). */
 int64_t snnqp_launch_count(int reset);

@@ -38,6 +38,9 @@ namespace {
 #define UMMA_DBG(bit) false
 #endif
 
+// spike-tile skip statistics of the bit-packed path: [0] all-zero input tiles whose 36 MMAs were skipped, [1] tiles seen
+__device__ unsigned long long g_tile_skip[2];
+
 constexpr int kC = 128;
 constexpr int kWBytes = 9 * kC * kC;            // 147456
 constexpr int kTapBytes = kC * kC;              // 16384
@@ -114,6 +117,12 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   uint64_t *pk_full = acc_empty + 2;             // [kPkStages]
   uint64_t *pk_empty = pk_full + kPkStages;      // [kPkStages]
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(pk_empty + kPkStages);
+  // spike-tile skip (XBITS): zin[stage] = 1 if the whole input box of that stage is zero (written by the expanders,
+  // read by the MMA issuer), zacc[buffer] = 1 if the step of that accumulator buffer was skipped (MMA issuer ->
+  // epilogue), wz[warp] = per-expander-warp "saw a set bit"
+  volatile uint32_t *zin = tmem_slot + 1;
+  volatile uint32_t *zacc = zin + kStages;
+  volatile uint32_t *wz = zacc + 2;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -192,12 +201,26 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       ptx::mbar_wait(a_ready, 0);
       ptx::tc_fence_after();
       uint32_t step = 0;
+      unsigned long long n_tiles = 0, n_skipped = 0;
       for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
         for (int t = 0; t < a.T; ++t, ++step) {
           const uint32_t s = step & 1, ph = (step >> 1) & 1;
           const uint32_t si = step % kStages, phi = (step / kStages) & 1;
           ptx::mbar_wait(acc_empty + s, ph ^ 1);
           ptx::mbar_wait(in_full + si, phi);
+          if constexpr (XBITS) {
+            // Spike-tile skip: an all-zero input box contributes nothing -- no MMAs; the epilogue takes acc = 0.
+            // Plain (release) arrivals replace the two commits: nothing asynchronous was issued for this step.
+            const bool zero_tile = zin[si] != 0;
+            zacc[s] = zero_tile ? 1u : 0u;
+            ++n_tiles;
+            if (zero_tile) {
+              ++n_skipped;
+              ptx::mbar_arrive(in_empty + si);
+              ptx::mbar_arrive(acc_full + s);
+              continue;
+            }
+          }
           ptx::tc_fence_after();
           const uint32_t x_addr = ptx::smem_u32(stage_smem + si * kStageBytes);
           const uint32_t d_tmem = tmem_base + s * kAccStride;
@@ -235,6 +258,10 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           ptx::mma_commit(acc_full + s);   // accumulator ready for the epilogue
         }
       }
+      if (XBITS && n_tiles) {
+        atomicAdd(&g_tile_skip[0], n_skipped);
+        atomicAdd(&g_tile_skip[1], n_tiles);
+      }
     }
   } else if (warp >= kEpiWarps + 2) {
     // ===================== expanders (XBITS): packed bits -> u8 operand rows =====================
@@ -250,19 +277,42 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           ptx::mbar_wait(in_empty + si, phi ^ 1);
           const uint8_t *src = pk_smem + ps * kPkStageBytes;
           uint8_t *dst = stage_smem + si * kStageBytes;
-          for (int task = et; task < ntask; task += 32 * kExpWarps) {
-            const int r = task >> 1, hf = task & 1;
-            const uint2 pkd = *reinterpret_cast<const uint2 *>(src + r * 16 + hf * 8);
-            uint8_t *row = dst + r * 128;
+          // pass 1: this thread's packed words (<= kMaxTasks of them, kept in registers) and whether any bit is set
+          constexpr int kMaxTasks = 5;          // ceil(2 * 272 / 128): the largest box is 4 x 66 + slack positions
+          uint2 pkd[kMaxTasks];
+          uint32_t any = 0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {                           // 16 channels = one 16-byte chunk
-              const uint32_t h16 = ((k & 2) ? pkd.y : pkd.x) >> ((k & 1) * 16);
-              uint4 o;
-              o.x = ((h16 & 0xFu) * 0x00204081u) & 0x01010101u;
-              o.y = (((h16 >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
-              o.z = (((h16 >> 8) & 0xFu) * 0x00204081u) & 0x01010101u;
-              o.w = (((h16 >> 12) & 0xFu) * 0x00204081u) & 0x01010101u;
-              *reinterpret_cast<uint4 *>(row + ((((hf << 2) | k) ^ (r & 7)) << 4)) = o;
+          for (int i = 0; i < kMaxTasks; ++i) {
+            const int task = et + i * 32 * kExpWarps;
+            pkd[i] = task < ntask ? *reinterpret_cast<const uint2 *>(src + (task >> 1) * 16 + (task & 1) * 8) : make_uint2(0u, 0u);
+            any |= pkd[i].x | pkd[i].y;
+          }
+          any = __reduce_or_sync(0xffffffffu, any);
+          if (lane == 0) wz[warp - (kEpiWarps + 2)] = any;
+          ptx::named_bar_sync(1, 32 * kExpWarps);
+          uint32_t tile_any = 0;
+#pragma unroll
+          for (int i = 0; i < kExpWarps; ++i) tile_any |= wz[i];
+          ptx::named_bar_sync(2, 32 * kExpWarps);        // wz is rewritten next step
+          if (et == 0) zin[si] = tile_any ? 0u : 1u;
+          if (tile_any) {
+#pragma unroll
+            for (int i = 0; i < kMaxTasks; ++i) {
+              const int task = et + i * 32 * kExpWarps;
+              if (task < ntask) {
+                const int r = task >> 1, hf = task & 1;
+                uint8_t *row = dst + r * 128;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {                           // 16 channels = one 16-byte chunk
+                  const uint32_t h16 = ((k & 2) ? pkd[i].y : pkd[i].x) >> ((k & 1) * 16);
+                  uint4 o;
+                  o.x = ((h16 & 0xFu) * 0x00204081u) & 0x01010101u;
+                  o.y = (((h16 >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
+                  o.z = (((h16 >> 8) & 0xFu) * 0x00204081u) & 0x01010101u;
+                  o.w = (((h16 >> 12) & 0xFu) * 0x00204081u) & 0x01010101u;
+                  *reinterpret_cast<uint4 *>(row + ((((hf << 2) | k) ^ (r & 7)) << 4)) = o;
+                }
+              }
             }
           }
           ptx::fence_proxy_async();          // generic-proxy writes -> visible to the tensor core (async proxy)
@@ -316,6 +366,7 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         const uint32_t s = step & 1, ph = (step >> 1) & 1;
         ptx::mbar_wait(acc_full + s, ph);
         ptx::tc_fence_after();
+        const bool zstep = XBITS && zacc[s] != 0;
         if constexpr (FAST) {
           // Production epilogue, register-lean: the accumulators arrive in chunks of 2 rows x 16 columns (8 pooled
           // outputs), so a thread holds its 64 membranes + 32 accumulators (the TMEM buffer is released after the
@@ -331,9 +382,14 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             const int pr = ch / NCC, cc = ch % NCC;
             uint32_t a0[CW], a1[CW];
             const uint32_t taddr = lane_addr + s * kAccStride + (r0 + 2 * pr) * a.P + w0 + cc * CW;
-            SNNQP_TMEM_LD_X16(taddr, a0);
-            SNNQP_TMEM_LD_X16(taddr + a.P, a1);
-            ptx::tc_wait_ld();
+            if (!zstep) {
+              SNNQP_TMEM_LD_X16(taddr, a0);
+              SNNQP_TMEM_LD_X16(taddr + a.P, a1);
+              ptx::tc_wait_ld();
+            } else {
+#pragma unroll
+              for (int j = 0; j < CW; ++j) a0[j] = a1[j] = 0u;      // skipped all-zero tile: accumulators are 0
+            }
             if (ch == NCH - 1) {
               ptx::tc_fence_before();
               __syncwarp();
@@ -375,7 +431,10 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           const uint32_t taddr = lane_addr + s * kAccStride + (r0 + r) * a.P + w0;
-          if constexpr (WC == 32) { SNNQP_TMEM_LD_X32(taddr, acc[r]); } else { SNNQP_TMEM_LD_X16(taddr, acc[r]); }
+          if (zstep) {
+#pragma unroll
+            for (int j = 0; j < WC; ++j) acc[r][j] = 0u;
+          } else if constexpr (WC == 32) { SNNQP_TMEM_LD_X32(taddr, acc[r]); } else { SNNQP_TMEM_LD_X16(taddr, acc[r]); }
         }
         ptx::tc_wait_ld();
         ptx::tc_fence_before();
@@ -572,3 +631,17 @@ int launch_conv3x3_umma(const snnqp_block_params &p, const uint8_t *x, const int
 }
 
 }  // namespace snnqp
+
+extern "C" int snnqp_tile_skip_stats(int64_t *skipped, int64_t *total, int reset) {
+  using namespace snnqp;
+  if (int rc = require_device()) return rc;
+  unsigned long long h[2] = {0, 0};
+  SNNQP_CUDA(cudaMemcpyFromSymbol(h, g_tile_skip, sizeof(h)));
+  if (skipped) *skipped = (int64_t)h[0];
+  if (total) *total = (int64_t)h[1];
+  if (reset) {
+    const unsigned long long z[2] = {0, 0};
+    SNNQP_CUDA(cudaMemcpyToSymbol(g_tile_skip, z, sizeof(z)));
+  }
+  return SNNQP_OK;
+}

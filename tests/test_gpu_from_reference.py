@@ -213,8 +213,12 @@ def test_production_shape_chunk_296(cuda_lib, oracle_lib):
   l296 = _engine(v, m, chunk=296).forward(frd).cpu().numpy()
   l16 = _engine(v, m, chunk=16).forward(frd).cpu().numpy()
   assert np.array_equal(l296, l16)
-  lfast = _engine(v, m, chunk=296, lif_mode=_lib.LIF_FAST).forward(frd).cpu().numpy()     # the bench's configuration
-  assert np.mean(np.abs(lfast - l296) > 1e-6) <= 0.01 and np.max(np.abs(lfast - l296)) <= 0.02
+  # the bench's configuration: single-rounding LIF in conv1.  ~4e-9 of its 3.1e9 pooled spikes flip (a handful in this
+  # batch); a flipped spike perturbs that sample's deeper layers, so a few samples move by a few output spikes
+  lfast = _engine(v, m, chunk=296, lif_mode=_lib.LIF_FAST).forward(frd).cpu().numpy()
+  changed = np.any(np.abs(lfast - l296) > 1e-6, axis=1)
+  assert changed.mean() <= 0.10 and np.max(np.abs(lfast - l296)) <= 0.02
+  assert np.mean(lfast.argmax(-1) == l296.argmax(-1)) >= 0.98
   pkd = ref_net.pack_network(v, bits, H)
   idx = [0, 295, 299]
   lo = ref_net.forward(pkd, fr[idx])

@@ -407,10 +407,7 @@ def run_dense(lib, x, wq, scale, bias, N, att=None, att_mod=0, impl=_lib.IMPL_SI
   _lib.check(lib.snnqp_spiking_dense_fwd(p, P(xs), P(attd), P(wq), P(scale), P(bias), P(spikes), P(u), P(acc),
                                          _lib.stream()))
   torch.cuda.synchronize()
-  sp = spikes.cpu().numpy()
-  if y_bits:
-    sp = np.unpackbits(sp, axis=-1, bitorder="little")
-  return sp, u.cpu().numpy(), acc.cpu().numpy()
+  return spikes.cpu().numpy(), u.cpu().numpy(), acc.cpu().numpy()
 
 
 @pytest.mark.parametrize("impl", impls())
@@ -754,3 +751,26 @@ def test_packed_file_round_trip_gives_identical_logits(cuda_lib, tmp_path):
   for k, t in cio._tensors_of(pk).items():
     assert torch.equal(t, cio._tensors_of(back)[k]), k
   assert np.array_equal(CextNetEngine(back).forward(fr).cpu().numpy(), want)
+
+
+def test_spike_tile_skip_on_structured_frames(cuda_lib):
+  """Spike-side tile skip: with bit-packed spikes an all-zero input box issues no MMAs.  On
+  spatially structured DVS-like frames (a moving blob on a silent sensor) most boxes are empty; the logits must be
+  exactly those of the u8 path (which never skips), and on i.i.d. frames nothing is skipped."""
+  import ctypes
+  from snnquantprune_b200 import CextNetEngine, pack_cextnet
+  bits, T, H, B = 8, 20, 128, 4
+  v = synthetic.make_variables(bits=bits, prune_percentage=0.5, T=T, H=H, seed=1)
+  pk = pack_cextnet(v, bits, T, H, device=DEV)
+  sk, tot = ctypes.c_int64(0), ctypes.c_int64(0)
+  rates = {}
+  for name, fr in (("blob", synthetic.make_frames_blob(B, T, H, H, seed=3)), ("iid", synthetic.make_frames(B, T, H, H, seed=3))):
+    frd = dev(fr)
+    want = CextNetEngine(pk, lif_mode=_lib.LIF_EXACT, packed_spikes=False).forward(frd).cpu().numpy()
+    _lib.check(cuda_lib.snnqp_tile_skip_stats(None, None, 1))
+    got = CextNetEngine(pk, lif_mode=_lib.LIF_EXACT, packed_spikes=True).forward(frd).cpu().numpy()
+    _lib.check(cuda_lib.snnqp_tile_skip_stats(ctypes.byref(sk), ctypes.byref(tot), 1))
+    assert np.array_equal(got, want), name
+    assert tot.value == B * T * (32 + 8 + 2)               # strips of conv2 / conv3 / conv4 per sample-step
+    rates[name] = sk.value / tot.value
+  assert rates["blob"] >= 0.5 and rates["iid"] == 0.0, rates
