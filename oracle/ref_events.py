@@ -3,7 +3,7 @@
 CPU restatement of the reference's event -> frame integration, "split by
 number" (/root/reference/examples/input_pipeline.py:142-219,
 ``preprocess_data_number``), and of the activation densities the model sows
-(/root/reference/examples/tcja/models.py:128-142).  PARITY UNPINNED: the
+(/root/reference/examples/tcja/models.py:128-142).  pinned to the executed reference: the
 reference ships no test or fixture for either and cannot run here (no
 tensorflow / jax); the restatement follows the source line by line.
 """

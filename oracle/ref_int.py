@@ -4,7 +4,7 @@ path -- what the CUDA kernels must reproduce bit for bit.
 Heavy loops live in ``csrc/snn_oracle.c`` (compiled by ``oracle/build.py`` with
 gcc, loaded through ctypes); this module holds the one-time pack / fold
 arithmetic and the layer wiring.  Reference citations are relative to
-/root/reference.  PARITY UNPINNED: see ``oracle/__init__.py``.
+/root/reference.  Pinned to the executed reference: see ``oracle/__init__.py``.
 """
 from __future__ import annotations
 

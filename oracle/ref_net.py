@@ -1,7 +1,6 @@
 """Oracle (test infrastructure): whole-network integer-path restatement of the
 TCJA-SNN eval forward (reference examples/tcja/models.py:101-257), built from
-the layer restatements in ``ref_int`` / ``ref_quant``.  PARITY UNPINNED: see
-``oracle/__init__.py``."""
+the layer restatements in ``ref_int`` / ``ref_quant``.  Pinned to the executed reference: see ``oracle/__init__.py``."""
 from __future__ import annotations
 
 from typing import Dict, Optional

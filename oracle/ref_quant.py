@@ -4,7 +4,7 @@ quantizer, calibrator, prune layer and magnitude-mask construction.
 Every function cites the reference lines it follows (paths relative to
 /root/reference).  All arithmetic is numpy float32 unless noted, mirroring
 ``jnp`` float32 semantics (``jnp.round`` == ``np.round`` == round-half-even).
-PARITY UNPINNED: see ``oracle/__init__.py``.
+Pinned to the executed reference: see ``oracle/__init__.py``.
 """
 from __future__ import annotations
 

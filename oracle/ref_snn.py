@@ -6,7 +6,7 @@ Contractions use torch-CPU fp32 ``conv2d`` / ``conv1d`` / ``matmul`` standing
 in for ``lax.conv_general_dilated`` / ``lax.dot_general``
 (flax_qconv.py:158-168, flax_qdense.py:87-89); everything else is numpy
 float32.  Paths cited are relative to /root/reference.
-PARITY UNPINNED: see ``oracle/__init__.py``.
+Pinned to the executed reference: see ``oracle/__init__.py``.
 """
 from __future__ import annotations
 

@@ -65,6 +65,7 @@ SIGNATURES = {
     "snnqp_events_to_frames": (_i, [_vp, _vp, _i, _i, _i, _i, _i64, _vp, _i, _vp, _vp]),
     "snnqp_slice_nonzeros": (_i, [_vp, _i, _i64, _i64, _vp, _vp]),
     "snnqp_slice_popcount": (_i, [_vp, _i, _i64, _i64, _vp, _vp]),
+    "snnqp_spiking_head_fwd": (_i, [_BP, _vp, _vp, _vp, _vp, _vp, _BP, _vp, _vp, _vp, _vp, _vp, _vp]),
     "snnqp_tile_skip_stats": (_i, [_vp, _vp, _i]),
     "snnqp_qlinear_fwd": (_i, [_vp, _i, _vp, _vp, _i64, _i, _i, _vp, _vp]),
     "snnqp_expand_frames_zsf": (_i, [_vp, _vp, _vp, C.c_uint32, _i64, _i, _vp, _vp]),

@@ -39,6 +39,12 @@ bool umma_conv1_supported(const snnqp_block_params &p, const float *att);
 int launch_conv1_umma(const snnqp_block_params &p, const uint8_t *x, const int8_t *wq4, const float *scale,
                       const float *bias, uint8_t *spikes, float *u_final, int32_t *acc_dump, cudaStream_t st);
 
+// umma_head.cu
+bool umma_head_supported(const snnqp_block_params *p1, const snnqp_block_params *p2);
+int launch_head_fused(const snnqp_block_params *p1, const uint8_t *x1, const int8_t *wq1_quad, const float *scale1,
+                      const float *bias1, uint8_t *y1, const snnqp_block_params *p2, const uint8_t *x2,
+                      const int8_t *wq2, const float *scale2, const float *bias2, uint8_t *y2, cudaStream_t st);
+
 static int check_conv(const snnqp_block_params *p, const void *x, const void *wq,
                       const void *scale, const void *bias, const char *fn) {
   if (!p || !x || !wq || !scale || !bias) return invalid("%s: null pointer", fn);
@@ -124,6 +130,29 @@ int snnqp_spiking_conv3x3_counts_fwd(const snnqp_block_params *p, const uint8_t 
   if (impl != SNNQP_IMPL_SIMT) return invalid("snnqp_spiking_conv3x3_fwd: impl=%d", p->impl);
   if (any_bits(p)) return bits_need_tcgen05("shape outside the tcgen05 envelope or SNNQP_IMPL_SIMT");
   return launch_conv3x3_simt(*p, x, att, wq, scale, bias, spikes, u_final, acc_dump, nullptr, spike_counts, st);
+}
+
+int snnqp_spiking_head_fwd(const snnqp_block_params *p1, const uint8_t *x1, const int8_t *wq1, const float *scale1,
+                           const float *bias1, uint8_t *spikes1, const snnqp_block_params *p2, const uint8_t *x2,
+                           const int8_t *wq2, const float *scale2, const float *bias2, uint8_t *spikes2, void *stream) {
+  if (int rc = require_device()) return rc;
+  const bool has1 = p1 && p1->B > 0, has2 = p2 && p2->B > 0;
+  if (!has1 && !has2) return invalid("snnqp_spiking_head_fwd: both halves are empty");
+  if (has1) {
+    if (int rc = check_conv(p1, x1, wq1, scale1, bias1, "snnqp_spiking_head_fwd (block 1)")) return rc;
+    if (!spikes1) return invalid("snnqp_spiking_head_fwd: null spikes1");
+  }
+  if (has2) {
+    if (int rc = check_conv(p2, x2, wq2, scale2, bias2, "snnqp_spiking_head_fwd (block 2)")) return rc;
+    if (!spikes2) return invalid("snnqp_spiking_head_fwd: null spikes2");
+  }
+  if (!umma_head_supported(has1 ? p1 : nullptr, has2 ? p2 : nullptr))
+    return unsupported("snnqp_spiking_head_fwd: block 1 must be Cin=2 -> 128 channels, W %% 32 == 0, u8 in / bit-packed "
+                       "out; block 2 128 -> 128 channels at 64x64 with bit-packed input; both standard LIF constants, "
+                       "pool = 1, equal T");
+  // conv1 blob = [Cout][32] tap-major followed by the 4 quad matrices [4][Cout][32]
+  return launch_head_fused(has1 ? p1 : nullptr, x1, has1 ? wq1 + (int64_t)p1->Cout * 32 : nullptr, scale1, bias1, spikes1,
+                           has2 ? p2 : nullptr, x2, wq2, scale2, bias2, spikes2, (cudaStream_t)stream);
 }
 
 int snnqp_qconv3x3_fwd(const snnqp_block_params *p, const uint8_t *x, const int8_t *wq,

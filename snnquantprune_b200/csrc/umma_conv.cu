@@ -121,8 +121,7 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   // read by the MMA issuer), zacc[buffer] = 1 if the step of that accumulator buffer was skipped (MMA issuer ->
   // epilogue), wz[warp] = per-expander-warp "saw a set bit"
   volatile uint32_t *zin = tmem_slot + 1;
-  volatile uint32_t *zacc = zin + kStages;
-  volatile uint32_t *wz = zacc + 2;
+  volatile uint32_t *zacc = zin + kStages * kExpWarps;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -211,7 +210,9 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           if constexpr (XBITS) {
             // Spike-tile skip: an all-zero input box contributes nothing -- no MMAs; the epilogue takes acc = 0.
             // Plain (release) arrivals replace the two commits: nothing asynchronous was issued for this step.
-            const bool zero_tile = zin[si] != 0;
+            bool zero_tile = true;
+#pragma unroll
+            for (int i = 0; i < kExpWarps; ++i) zero_tile = zero_tile && zin[si * kExpWarps + i] != 0;
             zacc[s] = zero_tile ? 1u : 0u;
             ++n_tiles;
             if (zero_tile) {
@@ -240,18 +241,19 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
               }
             }
           } else {
-            // block-sparse path: skip the all-zero K-slabs
-            uint32_t accumulate = 0;
-#pragma unroll 1
+            // block-sparse path: skip the all-zero K-slabs.  Fully unrolled with uniform predicates: a rolled loop
+            // (runtime tap / k arithmetic, descriptor table in local memory) issued one MMA per ~107 cycles and was
+            // SLOWER than the dense path (profiles/r2_sparse_paths.jsonl, first capture).
+            const int first_sl = __ffsll((long long)nz_mask) - 1;
+#pragma unroll
             for (int sl = 0; sl < 36; ++sl) {
               if (!((nz_mask >> sl) & 1) || UMMA_DBG(1)) continue;
               const int tap = sl >> 2, k = sl & 3;
               const uint64_t bd = bd0 + tap_off16[tap] + 2 * k;
               if (tap < kTmemTaps)
-                ptx::mma_i8_ts(d_tmem, tmem_base + kACol0 + sl * 8, bd, idesc, accumulate);
+                ptx::mma_i8_ts(d_tmem, tmem_base + kACol0 + sl * 8, bd, idesc, sl != first_sl);
               else
-                ptx::mma_i8(d_tmem, ad0 + ((tap - kTmemTaps) * kTapBytes + k * 32) / 16, bd, idesc, accumulate);
-              accumulate = 1;
+                ptx::mma_i8(d_tmem, ad0 + ((tap - kTmemTaps) * kTapBytes + k * 32) / 16, bd, idesc, sl != first_sl);
             }
           }
           ptx::mma_commit(in_empty + si);  // input stage reusable once these MMAs have read it
@@ -287,15 +289,11 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             pkd[i] = task < ntask ? *reinterpret_cast<const uint2 *>(src + (task >> 1) * 16 + (task & 1) * 8) : make_uint2(0u, 0u);
             any |= pkd[i].x | pkd[i].y;
           }
+          // per-warp verdict (no cross-warp barrier): the MMA issuer skips the step only if ALL expander warps saw
+          // zeros; a warp whose share is zero cannot know that, so it still writes its rows (as zeros, no arithmetic)
           any = __reduce_or_sync(0xffffffffu, any);
-          if (lane == 0) wz[warp - (kEpiWarps + 2)] = any;
-          ptx::named_bar_sync(1, 32 * kExpWarps);
-          uint32_t tile_any = 0;
-#pragma unroll
-          for (int i = 0; i < kExpWarps; ++i) tile_any |= wz[i];
-          ptx::named_bar_sync(2, 32 * kExpWarps);        // wz is rewritten next step
-          if (et == 0) zin[si] = tile_any ? 0u : 1u;
-          if (tile_any) {
+          if (lane == 0) zin[si * kExpWarps + (warp - (kEpiWarps + 2))] = any ? 0u : 1u;
+          {
 #pragma unroll
             for (int i = 0; i < kMaxTasks; ++i) {
               const int task = et + i * 32 * kExpWarps;
@@ -632,11 +630,15 @@ int launch_conv3x3_umma(const snnqp_block_params &p, const uint8_t *x, const int
 
 }  // namespace snnqp
 
+namespace snnqp { int head_skip_stats(unsigned long long *h, bool reset); }   // umma_head.cu
+
 extern "C" int snnqp_tile_skip_stats(int64_t *skipped, int64_t *total, int reset) {
   using namespace snnqp;
   if (int rc = require_device()) return rc;
-  unsigned long long h[2] = {0, 0};
+  unsigned long long h[2] = {0, 0}, hh[2] = {0, 0};
   SNNQP_CUDA(cudaMemcpyFromSymbol(h, g_tile_skip, sizeof(h)));
+  if (int rc = head_skip_stats(hh, reset != 0)) return rc;
+  h[0] += hh[0]; h[1] += hh[1];
   if (skipped) *skipped = (int64_t)h[0];
   if (total) *total = (int64_t)h[1];
   if (reset) {

@@ -2,11 +2,11 @@
 
     python tests/golden/make_golden.py
 
-The reference itself cannot be imported here (no jax / flax in the image,
-SURVEY.md F2), so these vectors come from the oracle restatements -- the float
-path in the reference's op order (oracle/ref_snn.py) and the integer path
-(oracle/ref_net.py), which must agree before anything is written.  PARITY
-UNPINNED against the real reference; see oracle/__init__.py."""
+Round-1 fixtures, kept as a second line of defence: these vectors come from the
+oracle restatements -- the float path in the reference's op order
+(oracle/ref_snn.py) and the integer path (oracle/ref_net.py), which must agree
+before anything is written.  The fixtures that pin the oracle itself to the
+executed reference are written by tests/golden/make_from_reference.py."""
 import hashlib
 import json
 import os

@@ -217,7 +217,7 @@ def test_production_shape_chunk_296(cuda_lib, oracle_lib):
   # batch); a flipped spike perturbs that sample's deeper layers, so a few samples move by a few output spikes
   lfast = _engine(v, m, chunk=296, lif_mode=_lib.LIF_FAST).forward(frd).cpu().numpy()
   changed = np.any(np.abs(lfast - l296) > 1e-6, axis=1)
-  assert changed.mean() <= 0.10 and np.max(np.abs(lfast - l296)) <= 0.02
+  assert changed.mean() <= 0.10 and np.max(np.abs(lfast - l296)) <= 0.05       # <= 10 output spikes of T * 10 = 200
   assert np.mean(lfast.argmax(-1) == l296.argmax(-1)) >= 0.98
   pkd = ref_net.pack_network(v, bits, H)
   idx = [0, 295, 299]
