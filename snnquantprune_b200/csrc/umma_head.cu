@@ -11,8 +11,9 @@
 //                        [384,512) conv1 accumulators, 2 stages x (4 matrices x 16 quads)  TMEM: r2_conv2_tmem_split]
 //   shared memory        conv2 taps 1-8 (128 KB) + 2 expanded input stages (70 KB) + 3 packed input stages (13 KB)
 //                        conv1 operand ring (4 x 2 KB) + TMA staging ring (8 x 384 B)
-//   registers (setmaxnreg per warpgroup; 768 threads launched at 80):
-//                        conv2 epilogue 8 warps x 128 | conv1 epilogue 8 warps x 80 | issue warps 4 x 56 | expanders 4 x 40
+//   registers (setmaxnreg per warpgroup; 768 threads launched at 80 = 61440, and a CTA can only re-distribute what it
+//   was launched with: 8 x 32 x 120 + 8 x 32 x 80 + 8 x 32 x 40 = 61440):
+//                        conv2 epilogue 8 warps x 120 | conv1 epilogue 8 warps x 80 | issue warps 4 x 40 | expanders 4 x 40
 //
 // conv1 role: tiles of 16 pooling quads (2 output rows x 32 columns), contraction per quad as in umma_conv1.cu
 // (K = 32 patch values, four weight matrices, kind::f16 so the fp32 accumulator is the exact integer), LIF with the
@@ -53,6 +54,8 @@ constexpr int kT_C2W = 288, kT_C1W = 320, kT_C1Acc = 384;
 constexpr int kSmem = kC2SmemTaps * kTapBytes + kC2Stages * kC2StageBytes + kPkStages * kPkStageBytes +
                       kBStages * kBBytes + kStStages * kStBytes + 1024 /*barriers*/ + 1024 /*align*/;
 static_assert(kSmem <= 232448, "shared memory budget");
+static_assert((kC2SmemTaps * kTapBytes + kC2Stages * kC2StageBytes) % 1024 == 0 && kBBytes % 1024 == 0, "swizzled operands");
+static_assert(kPkStageBytes % 128 == 0 && kStBytes % 128 == 0, "TMA destinations");
 
 struct HeadArgs {
   // conv1: frames u8 [.][.][H][W][2] -> pooled bit-packed spikes
@@ -111,9 +114,9 @@ k_head_fused(const __grid_constant__ CUtensorMap tm1x, const __grid_constant__ C
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t *c2_w = smem;
   uint8_t *c2_stage = c2_w + kC2SmemTaps * kTapBytes;
-  uint8_t *c2_pk = c2_stage + kC2Stages * kC2StageBytes;
-  uint8_t *c1_b = c2_pk + kPkStages * kPkStageBytes;
-  uint8_t *c1_st = c1_b + kBStages * kBBytes;
+  uint8_t *c1_b = c2_stage + kC2Stages * kC2StageBytes;      // swizzled operands first: they need 1024-byte alignment
+  uint8_t *c2_pk = c1_b + kBStages * kBBytes;                // (absolute-address swizzle), the TMA-only rings 128
+  uint8_t *c1_st = c2_pk + kPkStages * kPkStageBytes;
   uint64_t *bars = reinterpret_cast<uint64_t *>(c1_st + kStStages * kStBytes);
   // conv2 barriers
   uint64_t *w_full = bars + 0, *a2_ready = bars + 1;
@@ -154,8 +157,8 @@ k_head_fused(const __grid_constant__ CUtensorMap tm1x, const __grid_constant__ C
   const int QH = a.H1 / 2;
 
   if (warp < kW_C1Epi) {
-    // =============================== conv2 epilogue (8 warps, 128 registers) ===============================
-    reg_inc<128>();
+    // =============================== conv2 epilogue (8 warps, 120 registers) ===============================
+    reg_inc<120>();
     const int q = warp & 3, g = warp >> 2;
     const int c = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -329,7 +332,7 @@ k_head_fused(const __grid_constant__ CUtensorMap tm1x, const __grid_constant__ C
     }
   } else if (warp < kW_C2Exp) {
    // the four issue warps form one warpgroup: one setmaxnreg for all of them, then the roles
-   reg_dec<56>();
+   reg_dec<40>();
    if (warp == kW_C2Tma) {
     // =============================== conv2 TMA producer ===============================
     if (a.items2 > 0 && ptx::elect_one()) {
