@@ -367,8 +367,8 @@ def dominant_kernel_roofline(eng, frames, args, dev):
   tpath = os.path.join(ROOT, "profiles", "r2_conv2_traffic.json")
   if os.path.exists(tpath):
     tj = json.load(open(tpath))          # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
-    if tj.get("samples_per_launch") == Bc and tj.get("T") == pk.T:
-      traffic = tj["dram_bytes_per_launch"]
+    if tj.get("T") == pk.T and eng.packed_spikes:
+      traffic = tj["dram_bytes_per_sample"] * Bc          # per launch, like `achieved` (capture: 148 samples per launch)
   achieved = ops / (ms / 1e3) / 1e12
   # Denominator: MEASURED_PEAKS.json has no int8 figure (HBM GB/s and dense bf16 only), so the int8 tensor-pipe
   # ceiling is measured live on this GPU by the library's own probe (back-to-back tcgen05.mma.kind::i8

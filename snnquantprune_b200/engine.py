@@ -85,9 +85,8 @@ class CextNetEngine:
       raise ValueError("packed_spikes needs the tcgen05 kernels: H = 128, 128 channels, impl != IMPL_SIMT")
     self.packed_spikes = in_envelope if packed_spikes is None else bool(packed_spikes)
     # conv1 of chunk k+1 and conv2 of chunk k in one persistent kernel (snnqp_spiking_head_fwd); needs the bit-packed
-    # layout and the standard LIF constants
-    self.fused_head = (self.packed_spikes and tau == 2.0 and v_threshold == 1.0 and v_reset == 0.0) \
-        if fused_head is None else bool(fused_head)
+    # layout and the standard LIF constants.  Off by default: see DESIGN.md section 4.6 for the measured state.
+    self.fused_head = False if fused_head is None else bool(fused_head)
     if self.fused_head and not self.packed_spikes:
       raise ValueError("fused_head needs packed_spikes")
     self.tau, self.v_th, self.v_reset = tau, v_threshold, v_reset
