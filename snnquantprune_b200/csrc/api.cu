@@ -1,6 +1,8 @@
 // C-ABI entry points of the fused spiking blocks: argument validation and
 // dispatch between the tcgen05 kernels (umma_conv.cu) and the dp4a kernels
 // (simt.cu).  See include/snnqp.h for the contract.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace snnqp {
@@ -22,6 +24,12 @@ int launch_eval_metrics(const float *logits, const int32_t *labels, int B, int c
 // umma_conv.cu
 bool umma_conv3x3_supported(const snnqp_block_params &p, const float *att);
 int launch_conv3x3_umma(const snnqp_block_params &p, const uint8_t *x, const int8_t *wq,
+                        const float *scale, const float *bias, uint8_t *spikes, float *u_final,
+                        int32_t *acc_dump, int32_t *counts, cudaStream_t st);
+// umma_conv_t.cu: the pad-free 16 x 8 tile formulation (preferred); umma_conv.cu's strip formulation stays for
+// A/B measurements (SNNQP_CONV_STRIPS=1) and as the conv2 role of the fused head kernel
+bool umma_conv3x3_tile_supported(const snnqp_block_params &p, const float *att);
+int launch_conv3x3_tile(const snnqp_block_params &p, const uint8_t *x, const int8_t *wq,
                         const float *scale, const float *bias, uint8_t *spikes, float *u_final,
                         int32_t *acc_dump, int32_t *counts, cudaStream_t st);
 // umma_att.cu
@@ -118,8 +126,12 @@ int snnqp_spiking_conv3x3_counts_fwd(const snnqp_block_params *p, const uint8_t 
     if (impl != SNNQP_IMPL_SIMT) return invalid("snnqp_spiking_conv3x3_fwd: impl=%d", p->impl);
     return launch_conv3x3_simt(*p, x, att, wq, scale, bias, spikes, u_final, acc_dump, nullptr, spike_counts, st);
   }
+  static const bool force_strips = getenv("SNNQP_CONV_STRIPS") && atoi(getenv("SNNQP_CONV_STRIPS")) != 0;
+  const bool tile_ok = !force_strips && umma_conv3x3_tile_supported(*p, att);
   if (impl == SNNQP_IMPL_AUTO)
-    impl = umma_conv3x3_supported(*p, att) ? SNNQP_IMPL_TCGEN05 : SNNQP_IMPL_SIMT;
+    impl = (tile_ok || umma_conv3x3_supported(*p, att)) ? SNNQP_IMPL_TCGEN05 : SNNQP_IMPL_SIMT;
+  if (impl == SNNQP_IMPL_TCGEN05 && tile_ok)
+    return launch_conv3x3_tile(*p, x, wq, scale, bias, spikes, u_final, (int32_t *)acc_dump, spike_counts, st);
   if (impl == SNNQP_IMPL_TCGEN05) {
     if (!umma_conv3x3_supported(*p, att))
       return unsupported("snnqp_spiking_conv3x3_fwd: tcgen05 path needs Cin=Cout=128, binary/count input, "

@@ -645,7 +645,10 @@ int launch_conv3x3_umma(const snnqp_block_params &p, const uint8_t *x, const int
 
 }  // namespace snnqp
 
-namespace snnqp { int head_skip_stats(unsigned long long *h, bool reset); }   // umma_head.cu
+namespace snnqp {
+int head_skip_stats(unsigned long long *h, bool reset);          // umma_head.cu
+int tile_kernel_skip_stats(unsigned long long *h, bool reset);   // umma_conv_t.cu
+}
 
 extern "C" int snnqp_tile_skip_stats(int64_t *skipped, int64_t *total, int reset) {
   using namespace snnqp;
@@ -653,6 +656,8 @@ extern "C" int snnqp_tile_skip_stats(int64_t *skipped, int64_t *total, int reset
   unsigned long long h[2] = {0, 0}, hh[2] = {0, 0};
   SNNQP_CUDA(cudaMemcpyFromSymbol(h, g_tile_skip, sizeof(h)));
   if (int rc = head_skip_stats(hh, reset != 0)) return rc;
+  h[0] += hh[0]; h[1] += hh[1];
+  if (int rc = tile_kernel_skip_stats(hh, reset != 0)) return rc;
   h[0] += hh[0]; h[1] += hh[1];
   if (skipped) *skipped = (int64_t)h[0];
   if (total) *total = (int64_t)h[1];

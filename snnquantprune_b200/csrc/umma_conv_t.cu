@@ -1,25 +1,19 @@
-// Fused SpikingBlock(QuantConv3x3 -> BN -> LIF [-> 2x2 max-pool]) for binary /
-// count inputs with Cin = Cout = 128, on the 5th-gen tensor cores:
-// tcgen05.mma.kind::i8 fed by TMA, int32 accumulators in TMEM, T loop inside a
-// persistent, warp-specialised kernel.  Reference semantics:
-// SpikingBlock.__call__ spiking_learning.py:441-472 with QuantConv
-// (flax_qconv.py:158-168), eval BatchNorm (examples/tcja/models.py:101-107),
-// multi_step_LIF (spiking_learning.py:404-416) and the pool (models.py:145-147).
+// Fused SpikingBlock(QuantConv3x3 -> BN -> LIF [-> 2x2 max-pool]) for binary / count inputs, Cin = Cout = 128:
+// the PAD-FREE tiling of the block in umma_conv.cu (same roles, rings, epilogue arithmetic, block-sparse and
+// spike-tile skip paths; reference semantics spiking_learning.py:441-472, flax_qconv.py:158-168,
+// examples/tcja/models.py:101-147).
 //
-// Mapping ("swapped" implicit GEMM, flat shifts):
-//   D[cout, pos] += sum_{tap, cin} Wq[tap][cout][cin] * X[pos + shift(tap)][cin]
-//   * A operand (M = 128 output channels) = packed weights, resident in shared
-//     memory for the CTA's lifetime: 9 taps x [128 rows x 128 B], 128B swizzle.
-//   * B operand (N = flat output positions) = one TMA box per (strip, timestep):
-//     (TH+2) input rows x (W+2) columns x 128 channels, zero-filled halo (TMA
-//     out-of-bounds fill) -> smem rows of 128 B at pitch P = W+2.  Tap (kh,kw)
-//     is the SAME buffer read from row offset kh*P + kw: the zero columns make
-//     the flat shift exact, so nothing is re-loaded or re-laid-out per tap.
-//   * D (TMEM): lane = output channel, column = flat position r*P + w; the two
-//     pad columns per row hold garbage that is never read.  Two accumulator
-//     buffers so the epilogue of step i overlaps the MMAs of step i+1.
-//   * Epilogue: 8 warps; a thread owns one channel x 64 positions, keeps their
-//     membrane potentials in registers across all T steps, pools 2x2 in-thread.
+// umma_conv.cu walks an image in strips of TH full rows and reads the operand at FLAT shifts of the (W+2)-pitch
+// box, so its MMAs are N = 144 wide of which 128 columns are real outputs (2 pad columns per row, rounded to 16):
+// 11 % of the issued tensor work is pad, its measured 3.9 POP/s is the ceiling of that layout.  Here a work item
+// is a 16 x 8 SPATIAL tile: N = 128 output positions n = g * 8 + j (g = tile row 0..15, j = tile column 0..7).
+// The TMA box is 18 rows x 10 columns x 128 channels (zero-filled halo), 128-byte rows at pitch 10; for tap
+// (kh, kw) tile row g is the 8 consecutive box rows starting at (g + kh) * 10 + kw -- exactly a K-major
+// 128B-swizzle operand whose 8-row groups are 10 rows (1280 B) apart: the UMMA descriptor's stride-byte-offset
+// carries the image pitch (SBO = 1280 instead of 1024), and because the swizzle is a function of absolute
+// shared-memory address bits (measured in round 1) the groups may start at any 128-byte row.  Every issued MMA
+// column is a real output: 36 MMAs of 128 x 128 x 32 per step instead of 128 x 144 x 32 (-11 % tensor time), the
+// halo re-read drops from 2x to 1.4x, one kernel shape serves every width (W % 8 == 0, H % 16 == 0).
 #include <mutex>
 
 #include "common.cuh"
@@ -39,19 +33,23 @@ namespace {
 #endif
 
 // spike-tile skip statistics of the bit-packed path: [0] all-zero input tiles whose 36 MMAs were skipped, [1] tiles seen
-__device__ unsigned long long g_tile_skip[2];
+__device__ unsigned long long g_tile_skip_t[2];
 
 constexpr int kC = 128;
 constexpr int kWBytes = 9 * kC * kC;            // 147456
 constexpr int kTapBytes = kC * kC;              // 16384
-constexpr int kStageBytes = 35840;              // >= (2P+2+N) rows * 128 B for every config, 1024-aligned
+constexpr int kTileH = 16, kTileW = 8;          // output tile
+constexpr int kBoxH = kTileH + 2, kBoxW = kTileW + 2, kBoxRows = kBoxH * kBoxW;   // 180 box positions
+constexpr int kN = kTileH * kTileW;             // 128 = MMA N
+constexpr int kSBO = kBoxW * 128;               // stride between the 8-row groups of the B operand: the box pitch
+constexpr int kStageBytes = 23552;              // >= 180 rows * 128 B, 1024-aligned
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = (kEpiWarps + 2) * 32;  // + TMA warp + MMA warp
 // Bit-packed input (SNNQP_SPIKES_BITS): TMA stages the packed tile (16 B per position), two expander warps turn
 // bits into the u8 K-major 128B-swizzled MMA operand (3 integer ops per 4 bytes: nibble * 0x00204081 & 0x01010101).
 constexpr int kExpWarps = 4;
 constexpr int kThreadsX = kThreads + kExpWarps * 32;
-constexpr int kPkStages = 4, kPkStageBytes = 4352;   // >= (TH+2) * (W+2) * 16 B for every config, 128-aligned
+constexpr int kPkStages = 4, kPkStageBytes = 2944;   // >= 180 * 16 B, 128-aligned
 constexpr int kTmemCols = 512;
 // Weights (A operand) of the first kTmemTaps taps live in TENSOR MEMORY for the CTA's lifetime: with N = 144 an
 // SS-mode MMA pulls (128 + 144) * 32 B from shared memory per 72 cycles (94 % of the 128 B/cycle port, measured
@@ -59,7 +57,7 @@ constexpr int kTmemCols = 512;
 // 7 taps x 4 K-steps x 8 columns = 512 exactly.  The last two taps stay in shared memory (32 KB).
 // (template parameters TT = taps in TMEM, ST = input ring depth; production 7 / 4.  Other splits exist to measure
 // how much of the TMEM the layer really needs: tools/time_conv2_variants.py, profiles/r2_conv2_tmem_split.txt)
-constexpr int kAccStride = 144;                 // TMEM column offset of accumulator buffer 1
+constexpr int kAccStride = 128;                 // TMEM column offset of accumulator buffer 1
 constexpr int kACol0 = 2 * kAccStride;          // first TMEM column of the resident weights
 constexpr int smem_bytes_for(int tt, int st, bool xbits = false) {
   return (9 - tt) * kTapBytes + st * kStageBytes + (xbits ? kPkStages * kPkStageBytes : 0) + 1024 /*barriers*/ + 1024 /*align slack*/;
@@ -67,8 +65,7 @@ constexpr int smem_bytes_for(int tt, int st, bool xbits = false) {
 
 struct UmmaArgs {
   int T, B, H, W;
-  int P, N;                  // pitch W+2, MMA N
-  int strips, total_items;
+  int tiles_x, tiles_per_img, total_items;
   int64_t y_stride_t, y_stride_b;
   float tau, v_th, v_reset;
   int pool;
@@ -76,7 +73,6 @@ struct UmmaArgs {
   int tb_swapped;            // tensor-map dims 3/4 are (b, t) instead of (t, b)
   int one;                   // always 1 (runtime operand of the magic-number IMAD, see epilogue.cuh)
   int y_bits;                // 1: emit bit-packed spikes (production variants only)
-  int box_rows;              // (TH + 2) * P: positions of one input box
   int debug;                 // SNNQP_UMMA_DEBUG: bit0 skip MMA issue, bit1 skip epilogue math (timing bisection only)
   uint32_t stage_tx_bytes;
   const float *scale, *bias;
@@ -88,20 +84,14 @@ struct UmmaArgs {
   const int8_t *wq;          // packed weights [9][128][128] (read directly for the TMEM-resident taps)
 };
 
-template <int WCFG> struct Cfg;
-template <> struct Cfg<64> { static constexpr int TH = 2, R = 2, WC = 32; };
-template <> struct Cfg<32> { static constexpr int TH = 4, R = 2, WC = 32; };
-template <> struct Cfg<16> { static constexpr int TH = 8, R = 4, WC = 16; };
-
 // FAST: standard LIF constants (tau 2, threshold 1, reset 0), pooled output, no
 // instrumentation outputs -- the production variant; !FAST handles everything else.
-template <int WCFG, bool FAST, bool COUNTS, int kTmemTaps = 7, int kStages = 4, bool XBITS = false>
+template <bool FAST, bool COUNTS, bool XBITS>
 __global__ void __launch_bounds__(XBITS ? kThreadsX : kThreads, 1)
-k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+k_conv3x3_tile(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                const UmmaArgs a) {
+  constexpr int kTmemTaps = 7, kStages = 4;
   constexpr int kWSmemBytes = (9 - kTmemTaps) * kTapBytes;
-  using CF = Cfg<WCFG>;
-  constexpr int TH = CF::TH, R = CF::R, WC = CF::WC;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t *w_smem = smem;
@@ -161,19 +151,20 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         ptx::tma_load_2d(w_smem + (tap - kTmemTaps) * kTapBytes, &tmap_w, w_full, 0, tap * kC);
       uint32_t step = 0;
       for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
-        const int b = item / a.strips, h0 = (item % a.strips) * TH;
+        const int b = item / a.tiles_per_img, tl = item % a.tiles_per_img;
+        const int h0 = (tl / a.tiles_x) * kTileH, x0 = (tl % a.tiles_x) * kTileW;
         for (int t = 0; t < a.T; ++t, ++step) {
           if constexpr (XBITS) {
             const uint32_t s = step % kPkStages, ph = (step / kPkStages) & 1;
             ptx::mbar_wait(pk_empty + s, ph ^ 1);
             ptx::mbar_expect_tx(pk_full + s, a.stage_tx_bytes);
-            ptx::tma_load_5d(pk_smem + s * kPkStageBytes, &tmap_x, pk_full + s, 0, -1, h0 - 1,
+            ptx::tma_load_5d(pk_smem + s * kPkStageBytes, &tmap_x, pk_full + s, 0, x0 - 1, h0 - 1,
                              a.tb_swapped ? b : t, a.tb_swapped ? t : b);
           } else {
             const uint32_t s = step % kStages, ph = (step / kStages) & 1;
             ptx::mbar_wait(in_empty + s, ph ^ 1);
             ptx::mbar_expect_tx(in_full + s, a.stage_tx_bytes);
-            ptx::tma_load_5d(stage_smem + s * kStageBytes, &tmap_x, in_full + s, 0, -1, h0 - 1,
+            ptx::tma_load_5d(stage_smem + s * kStageBytes, &tmap_x, in_full + s, 0, x0 - 1, h0 - 1,
                              a.tb_swapped ? b : t, a.tb_swapped ? t : b);
           }
         }
@@ -191,20 +182,22 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         for (int i = 0; i < 36; ++i) nz_mask |= (uint64_t)(a.slab_nz[i] != 0) << i;
         if (nz_mask == 0) nz_mask = 1;   // keep one (all-zero) slab so the accumulator is still cleared
       }
-      const uint32_t idesc = ptx::make_idesc_i8(128, a.N, /*A = weights s8*/ true, /*B = inputs u8*/ false);
+      const uint32_t idesc = ptx::make_idesc_i8(128, kN, /*A = weights s8*/ true, /*B = inputs u8*/ false);
       const uint32_t w_addr = ptx::smem_u32(w_smem);
-      const uint64_t desc_hi = ptx::make_desc_sw128(0, 0);
+      const uint64_t desc_hi = ptx::make_desc_sw128(0, 0);                 // A (weights): 8-row groups 1024 B apart
       const uint64_t ad0 = desc_hi + (w_addr >> 4);
+      // B (activations): same layout, but the 8-row groups (tile rows) are one box pitch apart
+      const uint64_t bdesc_hi = (desc_hi & ~((uint64_t)0x3FFF << 32)) | ((uint64_t)(kSBO >> 4) << 32);
       uint32_t tap_off16[9];                       // (kh * P + kw) rows of 128 B, in 16-byte units
 #pragma unroll
-      for (int tap = 0; tap < 9; ++tap) tap_off16[tap] = (uint32_t)(((tap / 3) * a.P + (tap % 3)) * 8);
+      for (int tap = 0; tap < 9; ++tap) tap_off16[tap] = (uint32_t)(((tap / 3) * kBoxW + (tap % 3)) * 8);
       const bool dense_path = ((nz_mask & 0xFFFFFFFFFull) == 0xFFFFFFFFFull) && !UMMA_DBG(1);
       int n_slabs = 0;
       if (!dense_path) {
         for (int sl = 0; sl < 36; ++sl) {
           if (!((nz_mask >> sl) & 1) || UMMA_DBG(1)) continue;
           const int tap = sl >> 2, k = sl & 3;
-          const uint32_t boff = (uint32_t)(((tap / 3) * a.P + (tap % 3)) * 8 + 2 * k);
+          const uint32_t boff = (uint32_t)(((tap / 3) * kBoxW + (tap % 3)) * 8 + 2 * k);
           if (tap < kTmemTaps) slist[n_slabs] = make_uint2(tmem_base + kACol0 + sl * 8, (boff << 1) | 1u);
           else slist[n_slabs] = make_uint2((w_addr + (tap - kTmemTaps) * kTapBytes + k * 32) >> 4, boff << 1);
           ++n_slabs;
@@ -242,7 +235,7 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           const uint32_t d_tmem = tmem_base + s * kAccStride;
           // descriptors: constant high half; the 14-bit start-address field (16-byte units) is the only
           // part that changes, and shared-memory addresses never carry out of it
-          const uint64_t bd0 = desc_hi + (x_addr >> 4);
+          const uint64_t bd0 = bdesc_hi + (x_addr >> 4);
           if (dense_path) {
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
@@ -276,15 +269,15 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         }
       }
       if (XBITS && n_tiles) {
-        atomicAdd(&g_tile_skip[0], n_skipped);
-        atomicAdd(&g_tile_skip[1], n_tiles);
+        atomicAdd(&g_tile_skip_t[0], n_skipped);
+        atomicAdd(&g_tile_skip_t[1], n_tiles);
       }
     }
   } else if (warp >= kEpiWarps + 2) {
     // ===================== expanders (XBITS): packed bits -> u8 operand rows =====================
     if constexpr (XBITS) {
       const int et = threadIdx.x - (kEpiWarps + 2) * 32;          // 0 .. 32 * kExpWarps - 1
-      const int ntask = 2 * a.box_rows;                           // (position, 64-channel half)
+      constexpr int ntask = 2 * kBoxRows;                         // (position, 64-channel half)
       uint32_t step = 0;
       for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
         for (int t = 0; t < a.T; ++t, ++step) {
@@ -295,7 +288,7 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           const uint8_t *src = pk_smem + ps * kPkStageBytes;
           uint8_t *dst = stage_smem + si * kStageBytes;
           // pass 1: this thread's packed words (<= kMaxTasks of them, kept in registers) and whether any bit is set
-          constexpr int kMaxTasks = 5;          // ceil(2 * 272 / 128): the largest box is 4 x 66 + slack positions
+          constexpr int kMaxTasks = (ntask + 32 * kExpWarps - 1) / (32 * kExpWarps);
           uint2 pkd[kMaxTasks];
           uint32_t any = 0;
 #pragma unroll
@@ -342,8 +335,7 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     const int q = warp & 3, g = warp >> 2;          // TMEM lane quarter, column group
     const int c = q * 32 + lane;                    // output channel
     const float sc = a.scale[c], bi = a.bias[c];
-    const int r0 = (WCFG == 64) ? 0 : g * R;        // first strip row of this thread
-    const int w0 = (WCFG == 64) ? g * WC : 0;       // first column of this thread
+    // this thread's 64 outputs: tile rows 8g .. 8g+7 (accumulator columns 64g .. 64g+63), all 8 tile columns
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const int Wo = a.pool ? a.W / 2 : a.W;
     {
@@ -367,72 +359,65 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(a_ready);
     }
-    float u[R][WC];                 // membranes: in registers for all T steps of a strip
+    float u[8][8];                  // membranes [tile row - 8g][tile column]: in registers for all T steps of a tile
     uint32_t step = 0;
     for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
-      const int b = item / a.strips, h0 = (item % a.strips) * TH;
+      const int b = item / a.tiles_per_img, tl = item % a.tiles_per_img;
+      const int h0 = (tl / a.tiles_x) * kTileH + 8 * g, x0 = (tl % a.tiles_x) * kTileW;   // first output row / column of this thread
 #pragma unroll
-      for (int r = 0; r < R; ++r)
+      for (int r = 0; r < 8; ++r)
 #pragma unroll
-        for (int j = 0; j < WC; ++j) u[r][j] = 0.0f;   // zero carry (spiking_learning.py:464-472)
+        for (int j = 0; j < 8; ++j) u[r][j] = 0.0f;   // zero carry (spiking_learning.py:464-472)
       for (int t = 0; t < a.T; ++t, ++step) {
         const uint32_t s = step & 1, ph = (step >> 1) & 1;
         ptx::mbar_wait(acc_full + s, ph);
         ptx::tc_fence_after();
         const bool zstep = XBITS && zacc[s] != 0;
+        const uint32_t tcol = lane_addr + s * kAccStride + 64 * g;
         if constexpr (FAST) {
-          // Production epilogue, register-lean: the accumulators arrive in chunks of 2 rows x 16 columns (8 pooled
-          // outputs), so a thread holds its 64 membranes + 32 accumulators (the TMEM buffer is released after the
-          // last chunk is in registers; the MMAs of the next step run on the other buffer meanwhile).
-          // I2FP conversion: exact for every int32 accumulator (any uint8 input).
-          constexpr int CW = 16, NCC = WC / CW, NCH = (R / 2) * NCC;
+          // Production epilogue: accumulators in chunks of 16 columns = 2 tile rows x 8 columns = 4 pooled outputs;
+          // the TMEM buffer is released once the last chunk is in registers.  I2FP: exact for every int32.
           const LifParams<true> lifs{2.0f, 1.0f, 0.0f};
           int nspk = 0;
           uint32_t mine = 0;          // y_bits: the 32-channel word of pooled position `lane` (16 per thread-step)
-          uint8_t *y0 = a.spikes + (int64_t)t * a.y_stride_t + (int64_t)b * a.y_stride_b + c;
 #pragma unroll
-          for (int ch = 0; ch < NCH; ++ch) {
-            const int pr = ch / NCC, cc = ch % NCC;
-            uint32_t a0[CW], a1[CW];
-            const uint32_t taddr = lane_addr + s * kAccStride + (r0 + 2 * pr) * a.P + w0 + cc * CW;
+          for (int ch = 0; ch < 4; ++ch) {
+            uint32_t av[16];
             if (!zstep) {
-              SNNQP_TMEM_LD_X16(taddr, a0);
-              SNNQP_TMEM_LD_X16(taddr + a.P, a1);
+              SNNQP_TMEM_LD_X16(tcol + 16 * ch, av);
               ptx::tc_wait_ld();
             } else {
 #pragma unroll
-              for (int j = 0; j < CW; ++j) a0[j] = a1[j] = 0u;      // skipped all-zero tile: accumulators are 0
+              for (int j = 0; j < 16; ++j) av[j] = 0u;      // skipped all-zero tile: accumulators are 0
             }
-            if (ch == NCH - 1) {
+            if (ch == 3) {
               ptx::tc_fence_before();
               __syncwarp();
               if (lane == 0) ptx::mbar_arrive(acc_empty + s);        // TMEM buffer free for step + 2
             }
-            uint8_t *yrow = y0 + ((int64_t)((h0 + r0 + 2 * pr) >> 1) * Wo + (w0 >> 1)) * kC;
+            uint8_t *yrow = a.spikes + (int64_t)t * a.y_stride_t + (int64_t)b * a.y_stride_b + c +
+                            ((int64_t)((h0 >> 1) + ch) * Wo + (x0 >> 1)) * kC;
 #pragma unroll
-            for (int p8 = 0; p8 < CW / 2; ++p8) {
-              const int pc = cc * (CW / 2) + p8;
+            for (int pc = 0; pc < 4; ++pc) {
               bool any = false;
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const int r = 2 * pr + (e >> 1), j = 2 * pc + (e & 1);
-                const uint32_t av = (e >> 1) ? a1[2 * p8 + (e & 1)] : a0[2 * p8 + (e & 1)];
-                const bool sp = lifs.step(u[r][j], __fmaf_rn((float)(int32_t)av, sc, bi));
+                const int r = 2 * ch + (e >> 1), j = 2 * pc + (e & 1);
+                const bool sp = lifs.step(u[r][j], __fmaf_rn((float)(int32_t)av[8 * (e >> 1) + j], sc, bi));
                 any |= sp;
                 if constexpr (COUNTS) nspk += sp ? 1 : 0;
               }
               if (a.y_bits) {
                 const uint32_t bal = __ballot_sync(0xffffffffu, any);
-                if (lane == pr * (WC / 2) + pc) mine = bal;
+                if (lane == 4 * ch + pc) mine = bal;
               } else {
                 yrow[pc * kC] = any ? 1 : 0;
               }
             }
           }
-          if (a.y_bits && lane < (R / 2) * (WC / 2)) {
-            const int prl = lane / (WC / 2), pcl = lane % (WC / 2);
+          if (a.y_bits && lane < 16) {
             uint8_t *yw = a.spikes + (int64_t)t * a.y_stride_t + (int64_t)b * a.y_stride_b +
-                          ((int64_t)((h0 + r0 + 2 * prl) >> 1) * Wo + (w0 >> 1) + pcl) * (kC / 8) + q * 4;
+                          ((int64_t)((h0 >> 1) + (lane >> 2)) * Wo + (x0 >> 1) + (lane & 3)) * (kC / 8) + q * 4;
             *reinterpret_cast<uint32_t *>(yw) = mine;
           }
           if constexpr (COUNTS) {
@@ -440,70 +425,70 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           }
           continue;
         }
-        uint32_t acc[R][WC];
+        // generic / instrumented variant: any LIF constants, optional un-pooled output, membranes, accumulators
+        uint32_t acc[8][8];
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const uint32_t taddr = lane_addr + s * kAccStride + (r0 + r) * a.P + w0;
+        for (int r2 = 0; r2 < 4; ++r2) {
+          uint32_t av[16];
           if (zstep) {
 #pragma unroll
-            for (int j = 0; j < WC; ++j) acc[r][j] = 0u;
-          } else if constexpr (WC == 32) { SNNQP_TMEM_LD_X32(taddr, acc[r]); } else { SNNQP_TMEM_LD_X16(taddr, acc[r]); }
+            for (int j = 0; j < 16; ++j) av[j] = 0u;
+          } else {
+            SNNQP_TMEM_LD_X16(tcol + 16 * r2, av);
+            ptx::tc_wait_ld();
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[2 * r2 + (j >> 3)][j & 7] = av[j];
         }
-        ptx::tc_wait_ld();
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(acc_empty + s);        // TMEM buffer free for step + 2
-
         if (UMMA_DBG(2)) continue;
         const LifParams<false> lif{a.tau, a.v_th, a.v_reset};
-        uint32_t m[R];
+        uint32_t m[8];
+        int nspk = 0;
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
+        for (int r = 0; r < 8; ++r) {
           m[r] = 0;
 #pragma unroll
-          for (int j = 0; j < WC; ++j) {
+          for (int j = 0; j < 8; ++j) {
             const bool sp = lif.step(u[r][j], __fmaf_rn((float)(int32_t)acc[r][j], sc, bi));
             m[r] |= (sp ? 1u : 0u) << j;
           }
+          nspk += __popc(m[r]);
         }
-        if (a.counts) {
-          int nspk = 0;
-#pragma unroll
-          for (int r = 0; r < R; ++r) nspk += __popc(m[r]);
-          if (nspk) atomicAdd(a.counts + ((int64_t)b * a.T + t) * kC + c, nspk);
-        }
+        if (a.counts && nspk) atomicAdd(a.counts + ((int64_t)b * a.T + t) * kC + c, nspk);
         uint8_t *yb = a.spikes + (int64_t)t * a.y_stride_t + (int64_t)b * a.y_stride_b + c;
         if (a.pool) {
 #pragma unroll
-          for (int pr = 0; pr < R / 2; ++pr) {
+          for (int pr = 0; pr < 4; ++pr) {
             uint32_t mm = m[2 * pr] | m[2 * pr + 1];
             mm |= mm >> 1;
-            const int ho = (h0 + r0 + 2 * pr) >> 1;
 #pragma unroll
-            for (int pc = 0; pc < WC / 2; ++pc)
-              yb[((int64_t)ho * Wo + (w0 >> 1) + pc) * kC] = (mm >> (2 * pc)) & 1u;
+            for (int pc = 0; pc < 4; ++pc)
+              yb[((int64_t)((h0 >> 1) + pr) * Wo + (x0 >> 1) + pc) * kC] = (mm >> (2 * pc)) & 1u;
           }
         } else {
 #pragma unroll
-          for (int r = 0; r < R; ++r)
+          for (int r = 0; r < 8; ++r)
 #pragma unroll
-            for (int j = 0; j < WC; ++j)
-              yb[((int64_t)(h0 + r0 + r) * Wo + w0 + j) * kC] = (m[r] >> j) & 1u;
+            for (int j = 0; j < 8; ++j)
+              yb[((int64_t)(h0 + r) * Wo + x0 + j) * kC] = (m[r] >> j) & 1u;
         }
         if (a.acc_dump) {
 #pragma unroll
-          for (int r = 0; r < R; ++r)
+          for (int r = 0; r < 8; ++r)
 #pragma unroll
-            for (int j = 0; j < WC; ++j)
-              a.acc_dump[((((int64_t)t * a.B + b) * a.H + h0 + r0 + r) * a.W + w0 + j) * kC + c] = (int32_t)acc[r][j];
+            for (int j = 0; j < 8; ++j)
+              a.acc_dump[((((int64_t)t * a.B + b) * a.H + h0 + r) * a.W + x0 + j) * kC + c] = (int32_t)acc[r][j];
         }
       }
       if (a.u_final) {
 #pragma unroll
-        for (int r = 0; r < R; ++r)
+        for (int r = 0; r < 8; ++r)
 #pragma unroll
-          for (int j = 0; j < WC; ++j)
-            a.u_final[(((int64_t)b * a.H + h0 + r0 + r) * a.W + w0 + j) * kC + c] = u[r][j];
+          for (int j = 0; j < 8; ++j)
+            a.u_final[(((int64_t)b * a.H + h0 + r) * a.W + x0 + j) * kC + c] = u[r][j];
       }
     }
   }
@@ -518,20 +503,17 @@ k_conv3x3_umma(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 }
 
 // ---------------------------------------------------------------- host side ----
-int th_for(int W) { return W == 64 ? 2 : (W == 32 ? 4 : 8); }
-
 }  // namespace
 
-bool umma_conv3x3_supported(const snnqp_block_params &p, const float *att) {
+bool umma_conv3x3_tile_supported(const snnqp_block_params &p, const float *att) {
   if (att) return false;
   if (p.Cin != kC || p.Cout != kC) return false;
-  if (!(p.W == 64 || p.W == 32 || p.W == 16)) return false;
-  if (p.H % th_for(p.W) != 0) return false;
+  if (p.W % kTileW != 0 || p.H % kTileH != 0) return false;
   if (p.x_stride_t % 16 || p.x_stride_b % 16) return false;
   return true;
 }
 
-int launch_conv3x3_umma(const snnqp_block_params &p, const uint8_t *x, const int8_t *wq, const float *scale,
+int launch_conv3x3_tile(const snnqp_block_params &p, const uint8_t *x, const int8_t *wq, const float *scale,
                         const float *bias, uint8_t *spikes, float *u_final, int32_t *acc_dump, int32_t *counts,
                         cudaStream_t st) {
   EncodeTiledFn encode = tmap_encoder();
@@ -541,10 +523,6 @@ int launch_conv3x3_umma(const snnqp_block_params &p, const uint8_t *x, const int
   }
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(wq) & 15))
     return invalid("tcgen05 conv: x and wq must be 16-byte aligned");
-  const int TH = th_for(p.W), P = p.W + 2;
-  const int nflat = (TH - 1) * P + p.W;
-  const int N = (nflat + 15) / 16 * 16;
-  if ((2 * P + 2 + N) * 128 > kStageBytes) return unsupported("tcgen05 conv: stage buffer too small for W=%d", p.W);
 
   const bool xbits = p.x_format == SNNQP_SPIKES_BITS;
   const int cbytes = xbits ? kC / 8 : kC;       // bytes per position of x
@@ -554,12 +532,12 @@ int launch_conv3x3_umma(const snnqp_block_params &p, const uint8_t *x, const int
   const uint64_t st_b = p.B == 1 ? img * p.T : (uint64_t)p.x_stride_b;
   const bool tb_swapped = st_t > st_b;          // keep the outer strides non-decreasing
   // tensor maps are cached per (pointer, geometry): encoding costs microseconds of host time per launch
-  const TmapKey kx{x, {p.T, p.B, p.H, p.W, xbits ? 1 : 0, 0}, {(int64_t)st_t, (int64_t)st_b}};
+  const TmapKey kx{x, {p.T, p.B, p.H, p.W, xbits ? 1 : 0, 21}, {(int64_t)st_t, (int64_t)st_b}};
   const CUtensorMap *tmx_p = tmap_cache_get(kx, [&](CUtensorMap *tm) {
     cuuint64_t dims[5] = {(cuuint64_t)cbytes, (cuuint64_t)p.W, (cuuint64_t)p.H,
                           (cuuint64_t)(tb_swapped ? p.B : p.T), (cuuint64_t)(tb_swapped ? p.T : p.B)};
     cuuint64_t strides[4] = {(cuuint64_t)cbytes, (cuuint64_t)p.W * cbytes, tb_swapped ? st_b : st_t, tb_swapped ? st_t : st_b};
-    cuuint32_t box[5] = {(cuuint32_t)cbytes, (cuuint32_t)P, (cuuint32_t)(TH + 2), 1, 1};
+    cuuint32_t box[5] = {(cuuint32_t)cbytes, (cuuint32_t)kBoxW, (cuuint32_t)kBoxH, 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     return encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 5, const_cast<uint8_t *>(x), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, xbits ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
@@ -588,16 +566,15 @@ int launch_conv3x3_umma(const snnqp_block_params &p, const uint8_t *x, const int
 
   UmmaArgs a;
   a.T = p.T; a.B = p.B; a.H = p.H; a.W = p.W;
-  a.P = P; a.N = N;
-  a.strips = p.H / TH;
-  a.total_items = p.B * a.strips;
+  a.tiles_x = p.W / kTileW;
+  a.tiles_per_img = a.tiles_x * (p.H / kTileH);
+  a.total_items = p.B * a.tiles_per_img;
   a.y_stride_t = p.y_stride_t; a.y_stride_b = p.y_stride_b;
   a.tau = p.tau; a.v_th = p.v_threshold; a.v_reset = p.v_reset;
   a.pool = p.pool;
   a.tb_swapped = tb_swapped ? 1 : 0;
   a.one = 1;
   a.y_bits = p.y_format == SNNQP_SPIKES_BITS ? 1 : 0;
-  a.box_rows = (TH + 2) * P;
   a.base_off_mode = 0;   // the hardware applies the 128B swizzle on absolute smem address bits (measured)
 #ifdef SNNQP_C1_BISECT
   static const int dbg_env = getenv("SNNQP_UMMA_DEBUG") ? atoi(getenv("SNNQP_UMMA_DEBUG")) : 0;   // bisection switches (tools/)
@@ -605,8 +582,7 @@ int launch_conv3x3_umma(const snnqp_block_params &p, const uint8_t *x, const int
 #else
   a.debug = 0;
 #endif
-  a.stage_tx_bytes = (uint32_t)((TH + 2) * P * cbytes);
-  if (xbits && (int)a.stage_tx_bytes > kPkStageBytes) return unsupported("tcgen05 conv: packed stage too small for W=%d", p.W);
+  a.stage_tx_bytes = (uint32_t)(kBoxRows * cbytes);
   a.scale = scale; a.bias = bias;
   a.slab_nz = reinterpret_cast<const uint8_t *>(wq) + kWBytes;   // blob tail written by snnqp_pack_conv3x3
   a.spikes = spikes; a.u_final = u_final; a.acc_dump = acc_dump; a.counts = counts; a.wq = wq;
@@ -616,49 +592,35 @@ int launch_conv3x3_umma(const snnqp_block_params &p, const uint8_t *x, const int
   if (a.y_bits && !fast)
     return unsupported("tcgen05 conv: bit-packed output needs the production variant (standard LIF constants, pool = 1, "
                        "no u_final / acc_dump)");
-#define SNNQP_LAUNCH_UMMA(WV, FA, CO, XB)                                                                      \
+#define SNNQP_LAUNCH_TILE(FA, CO, XB)                                                                          \
   do {                                                                                                         \
     constexpr int kSm = smem_bytes_for(7, 4, XB);                                                              \
-    if (int rc = ensure_smem_attr<k_conv3x3_umma<WV, FA, CO, 7, 4, XB>>(kSm)) return rc;                       \
-    k_conv3x3_umma<WV, FA, CO, 7, 4, XB><<<grid, XB ? kThreadsX : kThreads, kSm, st>>>(tmx, tmw, a);           \
+    if (int rc = ensure_smem_attr<k_conv3x3_tile<FA, CO, XB>>(kSm)) return rc;                                 \
+    k_conv3x3_tile<FA, CO, XB><<<grid, XB ? kThreadsX : kThreads, kSm, st>>>(tmx, tmw, a);                     \
   } while (0)
-#define SNNQP_LAUNCH_UMMA_W(WV)                                             \
-  do {                                                                      \
-    if (xbits) {                                                            \
-      if (!fast) SNNQP_LAUNCH_UMMA(WV, false, false, true);                 \
-      else if (counts) SNNQP_LAUNCH_UMMA(WV, true, true, true);             \
-      else SNNQP_LAUNCH_UMMA(WV, true, false, true);                        \
-    } else {                                                                \
-      if (!fast) SNNQP_LAUNCH_UMMA(WV, false, false, false);                \
-      else if (counts) SNNQP_LAUNCH_UMMA(WV, true, true, false);            \
-      else SNNQP_LAUNCH_UMMA(WV, true, false, false);                       \
-    }                                                                       \
-  } while (0)
-  if (p.W == 64) SNNQP_LAUNCH_UMMA_W(64);
-  else if (p.W == 32) SNNQP_LAUNCH_UMMA_W(32);
-  else SNNQP_LAUNCH_UMMA_W(16);
-#undef SNNQP_LAUNCH_UMMA_W
-#undef SNNQP_LAUNCH_UMMA
-  SNNQP_POST_LAUNCH("k_conv3x3_umma");
+  if (xbits) {
+    if (!fast) SNNQP_LAUNCH_TILE(false, false, true);
+    else if (counts) SNNQP_LAUNCH_TILE(true, true, true);
+    else SNNQP_LAUNCH_TILE(true, false, true);
+  } else {
+    if (!fast) SNNQP_LAUNCH_TILE(false, false, false);
+    else if (counts) SNNQP_LAUNCH_TILE(true, true, false);
+    else SNNQP_LAUNCH_TILE(true, false, false);
+  }
+#undef SNNQP_LAUNCH_TILE
+  SNNQP_POST_LAUNCH("k_conv3x3_tile");
   return SNNQP_OK;
 }
 
 }  // namespace snnqp
 
-namespace snnqp { int head_skip_stats(unsigned long long *h, bool reset); }   // umma_head.cu
-
-extern "C" int snnqp_tile_skip_stats(int64_t *skipped, int64_t *total, int reset) {
-  using namespace snnqp;
-  if (int rc = require_device()) return rc;
-  unsigned long long h[2] = {0, 0}, hh[2] = {0, 0};
-  SNNQP_CUDA(cudaMemcpyFromSymbol(h, g_tile_skip, sizeof(h)));
-  if (int rc = head_skip_stats(hh, reset != 0)) return rc;
-  h[0] += hh[0]; h[1] += hh[1];
-  if (skipped) *skipped = (int64_t)h[0];
-  if (total) *total = (int64_t)h[1];
+namespace snnqp {
+int tile_kernel_skip_stats(unsigned long long *h, bool reset) {
+  SNNQP_CUDA(cudaMemcpyFromSymbol(h, g_tile_skip_t, 2 * sizeof(unsigned long long)));
   if (reset) {
     const unsigned long long z[2] = {0, 0};
-    SNNQP_CUDA(cudaMemcpyToSymbol(g_tile_skip, z, sizeof(z)));
+    SNNQP_CUDA(cudaMemcpyToSymbol(g_tile_skip_t, z, sizeof(z)));
   }
   return SNNQP_OK;
 }
+}  // namespace snnqp
