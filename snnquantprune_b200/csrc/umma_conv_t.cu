@@ -43,7 +43,13 @@ constexpr int kBoxH = kTileH + 2, kBoxW = kTileW + 2, kBoxRows = kBoxH * kBoxW; 
 constexpr int kN = kTileH * kTileW;             // 128 = MMA N
 constexpr int kSBO = kBoxW * 128;               // stride between the 8-row groups of the B operand: the box pitch
 constexpr int kStageBytes = 23552;              // >= 180 rows * 128 B, 1024-aligned
-constexpr int kEpiWarps = 8;
+// 16 epilogue warps: a thread owns one channel x 4 tile rows x 8 columns (32 membranes).  An epilogue warp is bound by
+// its own dependent-instruction latency (~4 cycles per instruction), not by issue slots: with 8 warps x 64 neurons a
+// step's epilogue took ~2500 cycles -- as long as its 36 MMAs (2304), which is why skipping MMAs (block-sparse weights,
+// all-zero spike tiles) gained nothing (profiles/r2_sparse_paths_8warp_epilogue.jsonl); 16 warps halve that latency.
+constexpr int kEpiWarps = 16;
+constexpr int kRowsPerThread = kTileH / (kEpiWarps / 4);     // 4
+constexpr int kColsPerThread = kRowsPerThread * kTileW;      // 32 accumulator columns per thread
 constexpr int kThreads = (kEpiWarps + 2) * 32;  // + TMA warp + MMA warp
 // Bit-packed input (SNNQP_SPIKES_BITS): TMA stages the packed tile (16 B per position), two expander warps turn
 // bits into the u8 K-major 128B-swizzled MMA operand (3 integer ops per 4 bytes: nibble * 0x00204081 & 0x01010101).
@@ -335,15 +341,13 @@ k_conv3x3_tile(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     const int q = warp & 3, g = warp >> 2;          // TMEM lane quarter, column group
     const int c = q * 32 + lane;                    // output channel
     const float sc = a.scale[c], bi = a.bias[c];
-    // this thread's 64 outputs: tile rows 8g .. 8g+7 (accumulator columns 64g .. 64g+63), all 8 tile columns
+    // this thread's 32 outputs: tile rows 4g .. 4g+3 (accumulator columns 32g .. 32g+31), all 8 tile columns
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const int Wo = a.pool ? a.W / 2 : a.W;
     {
       // one-time: this thread's weight row (output channel c) of the TMEM-resident taps -> tensor memory.
       // A-operand layout: lane = row, 32-bit column j of a K-step holds K bytes 4j .. 4j+3.
-      constexpr int kSplit = kTmemTaps < 4 ? kTmemTaps : 4;
-      const int tap0 = g == 0 ? 0 : kSplit, tap1 = g == 0 ? kSplit : kTmemTaps;
-      for (int tap = tap0; tap < tap1; ++tap) {
+      for (int tap = g; tap < kTmemTaps; tap += kEpiWarps / 4) {        // the column groups share the taps
         const int4 *wrow = reinterpret_cast<const int4 *>(a.wq + ((int64_t)tap * kC + c) * kC);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -359,13 +363,14 @@ k_conv3x3_tile(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(a_ready);
     }
-    float u[8][8];                  // membranes [tile row - 8g][tile column]: in registers for all T steps of a tile
+    constexpr int RT = kRowsPerThread;
+    float u[RT][8];                 // membranes [tile row - RT*g][tile column]: in registers for all T steps of a tile
     uint32_t step = 0;
     for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
       const int b = item / a.tiles_per_img, tl = item % a.tiles_per_img;
-      const int h0 = (tl / a.tiles_x) * kTileH + 8 * g, x0 = (tl % a.tiles_x) * kTileW;   // first output row / column of this thread
+      const int h0 = (tl / a.tiles_x) * kTileH + RT * g, x0 = (tl % a.tiles_x) * kTileW;   // first output row / column of this thread
 #pragma unroll
-      for (int r = 0; r < 8; ++r)
+      for (int r = 0; r < RT; ++r)
 #pragma unroll
         for (int j = 0; j < 8; ++j) u[r][j] = 0.0f;   // zero carry (spiking_learning.py:464-472)
       for (int t = 0; t < a.T; ++t, ++step) {
@@ -373,7 +378,7 @@ k_conv3x3_tile(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         ptx::mbar_wait(acc_full + s, ph);
         ptx::tc_fence_after();
         const bool zstep = XBITS && zacc[s] != 0;
-        const uint32_t tcol = lane_addr + s * kAccStride + 64 * g;
+        const uint32_t tcol = lane_addr + s * kAccStride + kColsPerThread * g;
         if constexpr (FAST) {
           // Production epilogue: accumulators in chunks of 16 columns = 2 tile rows x 8 columns = 4 pooled outputs;
           // the TMEM buffer is released once the last chunk is in registers.  I2FP: exact for every int32.
@@ -381,7 +386,7 @@ k_conv3x3_tile(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           int nspk = 0;
           uint32_t mine = 0;          // y_bits: the 32-channel word of pooled position `lane` (16 per thread-step)
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
+          for (int ch = 0; ch < RT / 2; ++ch) {
             uint32_t av[16];
             if (!zstep) {
               SNNQP_TMEM_LD_X16(tcol + 16 * ch, av);
@@ -390,7 +395,7 @@ k_conv3x3_tile(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 #pragma unroll
               for (int j = 0; j < 16; ++j) av[j] = 0u;      // skipped all-zero tile: accumulators are 0
             }
-            if (ch == 3) {
+            if (ch == RT / 2 - 1) {
               ptx::tc_fence_before();
               __syncwarp();
               if (lane == 0) ptx::mbar_arrive(acc_empty + s);        // TMEM buffer free for step + 2
@@ -415,7 +420,7 @@ k_conv3x3_tile(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
               }
             }
           }
-          if (a.y_bits && lane < 16) {
+          if (a.y_bits && lane < 2 * RT) {
             uint8_t *yw = a.spikes + (int64_t)t * a.y_stride_t + (int64_t)b * a.y_stride_b +
                           ((int64_t)((h0 >> 1) + (lane >> 2)) * Wo + (x0 >> 1) + (lane & 3)) * (kC / 8) + q * 4;
             *reinterpret_cast<uint32_t *>(yw) = mine;
@@ -426,9 +431,9 @@ k_conv3x3_tile(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           continue;
         }
         // generic / instrumented variant: any LIF constants, optional un-pooled output, membranes, accumulators
-        uint32_t acc[8][8];
+        uint32_t acc[RT][8];
 #pragma unroll
-        for (int r2 = 0; r2 < 4; ++r2) {
+        for (int r2 = 0; r2 < RT / 2; ++r2) {
           uint32_t av[16];
           if (zstep) {
 #pragma unroll
@@ -445,10 +450,10 @@ k_conv3x3_tile(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         if (lane == 0) ptx::mbar_arrive(acc_empty + s);        // TMEM buffer free for step + 2
         if (UMMA_DBG(2)) continue;
         const LifParams<false> lif{a.tau, a.v_th, a.v_reset};
-        uint32_t m[8];
+        uint32_t m[RT];
         int nspk = 0;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
+        for (int r = 0; r < RT; ++r) {
           m[r] = 0;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -461,7 +466,7 @@ k_conv3x3_tile(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         uint8_t *yb = a.spikes + (int64_t)t * a.y_stride_t + (int64_t)b * a.y_stride_b + c;
         if (a.pool) {
 #pragma unroll
-          for (int pr = 0; pr < 4; ++pr) {
+          for (int pr = 0; pr < RT / 2; ++pr) {
             uint32_t mm = m[2 * pr] | m[2 * pr + 1];
             mm |= mm >> 1;
 #pragma unroll
@@ -470,14 +475,14 @@ k_conv3x3_tile(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           }
         } else {
 #pragma unroll
-          for (int r = 0; r < 8; ++r)
+          for (int r = 0; r < RT; ++r)
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               yb[((int64_t)(h0 + r) * Wo + x0 + j) * kC] = (m[r] >> j) & 1u;
         }
         if (a.acc_dump) {
 #pragma unroll
-          for (int r = 0; r < 8; ++r)
+          for (int r = 0; r < RT; ++r)
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               a.acc_dump[((((int64_t)t * a.B + b) * a.H + h0 + r) * a.W + x0 + j) * kC + c] = (int32_t)acc[r][j];
@@ -485,7 +490,7 @@ k_conv3x3_tile(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       }
       if (a.u_final) {
 #pragma unroll
-        for (int r = 0; r < 8; ++r)
+        for (int r = 0; r < RT; ++r)
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             a.u_final[(((int64_t)b * a.H + h0 + r) * a.W + x0 + j) * kC + c] = u[r][j];
