@@ -197,7 +197,10 @@ k_conv3x3_tile(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       uint32_t tap_off16[9];                       // (kh * P + kw) rows of 128 B, in 16-byte units
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) tap_off16[tap] = (uint32_t)(((tap / 3) * kBoxW + (tap % 3)) * 8);
-      const bool dense_path = ((nz_mask & 0xFFFFFFFFFull) == 0xFFFFFFFFFull) && !UMMA_DBG(1);
+      // The list-driven skip loop costs ~150 issue cycles per MMA against 72 in the unrolled dense sequence (a lone
+      // issuing thread is bound by its dependent-instruction latency), so it only pays when at most a third of the 36
+      // slabs is left (measured, profiles/r2_sparse_paths.jsonl); otherwise the zero slabs are simply multiplied.
+      const bool dense_path = (__popcll(nz_mask & 0xFFFFFFFFFull) > 12) && !UMMA_DBG(1);
       int n_slabs = 0;
       if (!dense_path) {
         for (int sl = 0; sl < 36; ++sl) {
