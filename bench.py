@@ -403,9 +403,9 @@ def per_kernel_rooflines(eng, frames, ms_step, int8_peak_tops):
   specs = [
       ("conv1 fused block (k_conv1_umma: 128x128x2 -> 128, LIF, pool)", lambda: eng._conv(0, frames[:n], ws["s1"][:n], n, H, 2, 1),
        2 * 0.755 * scale, T * H * H * 2 / 1e6 + px(H // 2), n),
-      ("conv2 fused block (k_conv3x3_umma<64>)", lambda: eng._conv(1, ws["s1"][:n], ws["s2"][:n], n, H // 2, C, 1),
+      ("conv2 fused block (k_conv3x3_tile, 64x64x128 -> 128)", lambda: eng._conv(1, ws["s1"][:n], ws["s2"][:n], n, H // 2, C, 1),
        2 * 12.080 * scale, px(H // 2) + px(H // 4), n),
-      ("conv3 fused block (k_conv3x3_umma<32>)", lambda: eng._conv(2, ws["s2"][:n], ws["s3"][:n], n, H // 4, C, 1),
+      ("conv3 fused block (k_conv3x3_tile, 32x32x128 -> 128)", lambda: eng._conv(2, ws["s2"][:n], ws["s3"][:n], n, H // 4, C, 1),
        2 * 3.020 * scale, px(H // 4) + px(H // 8), n),
   ]
   out = []
@@ -430,7 +430,10 @@ def per_kernel_rooflines(eng, frames, ms_step, int8_peak_tops):
                 "tensor": {"achieved": tops, "peak": int8_peak_tops, "unit": "TOP/s", "frac": tops / int8_peak_tops},
                 "hbm": {"achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
                         "algorithmic_mb_per_sample": mb},
-                "bound": "tensor" if tops / int8_peak_tops > gbs / hbm else "issue slots of the LIF epilogue (neither roofline)"})
+                "bound": "tensor" if tops / int8_peak_tops > gbs / hbm else "hbm",
+                "limiter": ("issue slots of the LIF epilogue: 5.75 issued instructions per neuron-step, issue active 74 %, "
+                            "tensor pipe 13 % (profiles/r2_ncu_full_final.json) -- far from both rooflines by construction")
+                           if "conv1" in name else "tensor pipe (89 % active bit-packed, 95 % with u8 spikes)"})
   return out
 
 

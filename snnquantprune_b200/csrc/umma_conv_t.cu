@@ -41,6 +41,7 @@ constexpr int kTapBytes = kC * kC;              // 16384
 constexpr int kTileH = 16, kTileW = 8;          // output tile
 constexpr int kBoxH = kTileH + 2, kBoxW = kTileW + 2, kBoxRows = kBoxH * kBoxW;   // 180 box positions
 constexpr int kN = kTileH * kTileW;             // 128 = MMA N
+constexpr int kStagesBits = 6;                  // operand ring depth of the bit-packed variant (expanders run further ahead)
 constexpr int kSBO = kBoxW * 128;               // stride between the 8-row groups of the B operand: the box pitch
 constexpr int kStageBytes = 23552;              // >= 180 rows * 128 B, 1024-aligned
 // 16 epilogue warps: a thread owns one channel x 4 tile rows x 8 columns (32 membranes).  An epilogue warp is bound by
@@ -55,7 +56,7 @@ constexpr int kThreads = (kEpiWarps + 2) * 32;  // + TMA warp + MMA warp
 // bits into the u8 K-major 128B-swizzled MMA operand (3 integer ops per 4 bytes: nibble * 0x00204081 & 0x01010101).
 constexpr int kExpWarps = 4;
 constexpr int kThreadsX = kThreads + kExpWarps * 32;
-constexpr int kPkStages = 4, kPkStageBytes = 2944;   // >= 180 * 16 B, 128-aligned
+constexpr int kPkStages = 6, kPkStageBytes = 2944;   // >= 180 * 16 B, 128-aligned
 constexpr int kTmemCols = 512;
 // Weights (A operand) of the first kTmemTaps taps live in TENSOR MEMORY for the CTA's lifetime: with N = 144 an
 // SS-mode MMA pulls (128 + 144) * 32 B from shared memory per 72 cycles (94 % of the 128 B/cycle port, measured
@@ -96,7 +97,7 @@ template <bool FAST, bool COUNTS, bool XBITS>
 __global__ void __launch_bounds__(XBITS ? kThreadsX : kThreads, 1)
 k_conv3x3_tile(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                const UmmaArgs a) {
-  constexpr int kTmemTaps = 7, kStages = 4;
+  constexpr int kTmemTaps = 7, kStages = XBITS ? kStagesBits : 4;
   constexpr int kWSmemBytes = (9 - kTmemTaps) * kTapBytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -602,7 +603,7 @@ int launch_conv3x3_tile(const snnqp_block_params &p, const uint8_t *x, const int
                        "no u_final / acc_dump)");
 #define SNNQP_LAUNCH_TILE(FA, CO, XB)                                                                          \
   do {                                                                                                         \
-    constexpr int kSm = smem_bytes_for(7, 4, XB);                                                              \
+    constexpr int kSm = smem_bytes_for(7, XB ? kStagesBits : 4, XB);                                                              \
     if (int rc = ensure_smem_attr<k_conv3x3_tile<FA, CO, XB>>(kSm)) return rc;                                 \
     k_conv3x3_tile<FA, CO, XB><<<grid, XB ? kThreadsX : kThreads, kSm, st>>>(tmx, tmw, a);                     \
   } while (0)
