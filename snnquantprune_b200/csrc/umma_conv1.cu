@@ -305,6 +305,7 @@ k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
         w0 = __float_as_uint(s0);
         w1 = __float_as_uint(s1);
       };
+      const bool lb0 = lane & 1, lb1 = lane & 2, lb2 = lane & 4;
       uint32_t step = 0;
       for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
         const int tile = item % a.tiles_per_row, qh = (item / a.tiles_per_row) % QH;
@@ -335,16 +336,28 @@ k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
           if (a.y_bits) {
             // pooled spike of (quad, channel = lane) -> one ballot per quad = the 32-channel word of that position;
             // lane i keeps the word of quad i and the warp stores NQ words with one instruction
-            uint32_t mine = 0;
+            uint32_t bal[NQ];
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
               uint32_t w[4][2];
 #pragma unroll
               for (int j = 0; j < 4; ++j) lif_pair(u2[j][p], acc[j][2 * p], acc[j][2 * p + 1], w[j][0], w[j][1], j);
-              const uint32_t b0 = __ballot_sync(0xffffffffu, ((w[0][0] | w[1][0]) | (w[2][0] | w[3][0])) != 0u);
-              const uint32_t b1 = __ballot_sync(0xffffffffu, ((w[0][1] | w[1][1]) | (w[2][1] | w[3][1])) != 0u);
-              if (lane == 2 * p) mine = b0;
-              if (lane == 2 * p + 1) mine = b1;
+              bal[2 * p] = __ballot_sync(0xffffffffu, ((w[0][0] | w[1][0]) | (w[2][0] | w[3][0])) != 0u);
+              bal[2 * p + 1] = __ballot_sync(0xffffffffu, ((w[0][1] | w[1][1]) | (w[2][1] | w[3][1])) != 0u);
+            }
+            // lane i keeps quad i's word: a select tree on the lane-index bits (NQ - 1 selects, predicates hoisted out
+            // of the T loop) instead of one compare + predicated move per ballot
+            uint32_t mine;
+            if constexpr (NQ == 8) {
+              const uint32_t a0 = lb0 ? bal[1] : bal[0], a1 = lb0 ? bal[3] : bal[2], a2 = lb0 ? bal[5] : bal[4],
+                             a3 = lb0 ? bal[7] : bal[6];
+              const uint32_t c0 = lb1 ? a1 : a0, c1 = lb1 ? a3 : a2;
+              mine = lb2 ? c1 : c0;
+            } else {
+              mine = 0;
+#pragma unroll
+              for (int i = 0; i < NQ; ++i)
+                if (lane == i) mine = bal[i];
             }
             if (lane < NQ) *reinterpret_cast<uint32_t *>(yrow) = mine;
           } else {
