@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define SNNQP_ABI_VERSION 2
+#define SNNQP_ABI_VERSION 3
 
 #define SNNQP_OK 0
 #define SNNQP_ERR_INVALID 1      /* bad argument / unsupported shape           */
@@ -129,6 +129,11 @@ typedef struct snnqp_block_params {
   int32_t x_format;        /* SNNQP_SPIKES_*: layout of x (BITS: binary inputs, Cin % 32 == 0) */
   int32_t y_format;        /* SNNQP_SPIKES_*: layout of the emitted spikes        */
   int32_t lif_mode;        /* SNNQP_LIF_*                                          */
+  int32_t *y_popcount;     /* NULL, or device int32 [B][T], caller-zeroed: += the number of
+                            * emitted (pooled) spikes of each (b, t) -- the numerator of the input
+                            * density the reference sows for the NEXT layer (examples/tcja/
+                            * models.py:128-142), for free from the ballot words of the
+                            * bit-packed epilogues (y_format == SNNQP_SPIKES_BITS only)        */
 } snnqp_block_params;
 
 /* Spike tensor layouts (both channel-minor, strides in bytes):

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # SNNQP_LIB: developer switch for same-box A/B timing of two builds (tools/); the product path is the in-tree .so
 LIB_PATH = os.environ.get("SNNQP_LIB") or os.path.join(_HERE, "libsnnqp.so")
 
-ABI_VERSION = 2          # include/snnqp.h SNNQP_ABI_VERSION (block params carry x_format / y_format / lif_mode)
+ABI_VERSION = 3          # include/snnqp.h SNNQP_ABI_VERSION (block params carry x_format / y_format / lif_mode)
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
 SPIKES_U8, SPIKES_BITS = 0, 1
 LIF_EXACT, LIF_FAST = 0, 1
@@ -34,6 +34,7 @@ class BlockParams(C.Structure):
       ("tau", C.c_float), ("v_threshold", C.c_float), ("v_reset", C.c_float),
       ("pool", C.c_int32), ("impl", C.c_int32),
       ("x_format", C.c_int32), ("y_format", C.c_int32), ("lif_mode", C.c_int32),
+      ("y_popcount", C.c_void_p),
   ]
 
 

@@ -71,6 +71,11 @@ static int check_conv(const snnqp_block_params *p, const void *x, const void *wq
     return invalid("%s: lif_mode=%d", fn, p->lif_mode);
   return SNNQP_OK;
 }
+static int check_popcount(const snnqp_block_params *p) {
+  if (p->y_popcount && p->y_format != SNNQP_SPIKES_BITS)
+    return unsupported("y_popcount needs y_format == SNNQP_SPIKES_BITS (it is the popcount of the ballot words)");
+  return SNNQP_OK;
+}
 static bool any_bits(const snnqp_block_params *p) {
   return p->x_format == SNNQP_SPIKES_BITS || p->y_format == SNNQP_SPIKES_BITS;
 }
@@ -96,6 +101,7 @@ int snnqp_spiking_conv3x3_counts_fwd(const snnqp_block_params *p, const uint8_t 
   if (int rc = require_device()) return rc;
   if (int rc = check_conv(p, x, wq, scale, bias, "snnqp_spiking_conv3x3_fwd")) return rc;
   if (!spikes) return invalid("snnqp_spiking_conv3x3_fwd: null spikes");
+  if (int rc = check_popcount(p)) return rc;
   if (att && p->Cin == 2) return unsupported("snnqp_spiking_conv3x3_fwd: att with Cin=2");
   cudaStream_t st = (cudaStream_t)stream;
   int impl = p->impl;
@@ -185,8 +191,8 @@ int snnqp_spiking_dense_fwd(const snnqp_block_params *p, const uint8_t *x, const
   if (p->T <= 0 || p->B <= 0 || p->Cin <= 0 || p->Cout <= 0)
     return invalid("snnqp_spiking_dense_fwd: bad shape T=%d B=%d K=%d N=%d", p->T, p->B, p->Cin, p->Cout);
   if (!(p->tau > 0.f)) return invalid("snnqp_spiking_dense_fwd: tau must be > 0");
-  if (p->x_format != SNNQP_SPIKES_U8 || p->y_format != SNNQP_SPIKES_U8)
-    return unsupported("snnqp_spiking_dense_fwd: SNNQP_SPIKES_U8 only");
+  if (p->x_format != SNNQP_SPIKES_U8 || p->y_format != SNNQP_SPIKES_U8 || p->y_popcount)
+    return unsupported("snnqp_spiking_dense_fwd: SNNQP_SPIKES_U8 only, no y_popcount");
   const int k_pad = (p->Cin + 15) / 16 * 16;
   if (k_pad > 8192) return unsupported("snnqp_spiking_dense_fwd: K=%d too large (max 8192)", p->Cin);
   if (att && p->att_mod <= 0) return invalid("snnqp_spiking_dense_fwd: att_mod=%d", p->att_mod);

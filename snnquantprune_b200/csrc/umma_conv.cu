@@ -549,6 +549,7 @@ int launch_conv3x3_umma(const snnqp_block_params &p, const uint8_t *x, const int
   const int N = (nflat + 15) / 16 * 16;
   if ((2 * P + 2 + N) * 128 > kStageBytes) return unsupported("tcgen05 conv: stage buffer too small for W=%d", p.W);
 
+  if (p.y_popcount) return unsupported("tcgen05 conv (strip formulation): y_popcount is implemented by the tile kernel");
   const bool xbits = p.x_format == SNNQP_SPIKES_BITS;
   const int cbytes = xbits ? kC / 8 : kC;       // bytes per position of x
   // a size-1 dimension may carry any stride: give it a sane one

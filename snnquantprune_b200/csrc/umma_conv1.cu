@@ -65,6 +65,7 @@ struct Conv1Args {
   float tau, v_th, v_reset;
   int pool, tb_swapped, debug;
   int y_bits;                  // 1: emit bit-packed spikes (SNNQP_SPIKES_BITS), FAST variants only
+  int32_t *y_popcount;         // nullable [B][T]: += emitted spikes (y_bits only)
   const int8_t *wq4;           // [4][cout][32] row-major
   const float *scale, *bias;
   uint8_t *spikes;
@@ -360,6 +361,10 @@ k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
                 if (lane == i) mine = bal[i];
             }
             if (lane < NQ) *reinterpret_cast<uint32_t *>(yrow) = mine;
+            if (a.y_popcount) {          // density numerator of the next layer's input: popcount of the ballot words
+              const int n = __reduce_add_sync(0xffffffffu, lane < NQ ? __popc(mine) : 0);
+              if (lane == 0 && n) atomicAdd(a.y_popcount + (int64_t)b * a.T + t, n);
+            }
           } else {
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
@@ -496,6 +501,7 @@ int launch_conv1_umma(const snnqp_block_params &p, const uint8_t *x, const int8_
   a.tau = p.tau; a.v_th = p.v_threshold; a.v_reset = p.v_reset;
   a.pool = p.pool; a.tb_swapped = swapped ? 1 : 0;
   a.y_bits = p.y_format == SNNQP_SPIKES_BITS ? 1 : 0;
+  a.y_popcount = p.y_popcount;
   static const int dbg_env = getenv("SNNQP_C1_DEBUG") ? atoi(getenv("SNNQP_C1_DEBUG")) : 0;   // bisection switches (tools/)
   a.debug = dbg_env;
   a.wq4 = wq4; a.scale = scale; a.bias = bias;

@@ -80,6 +80,7 @@ struct UmmaArgs {
   int tb_swapped;            // tensor-map dims 3/4 are (b, t) instead of (t, b)
   int one;                   // always 1 (runtime operand of the magic-number IMAD, see epilogue.cuh)
   int y_bits;                // 1: emit bit-packed spikes (production variants only)
+  int32_t *y_popcount;       // nullable [B][T]: += emitted spikes (y_bits only)
   int debug;                 // SNNQP_UMMA_DEBUG: bit0 skip MMA issue, bit1 skip epilogue math (timing bisection only)
   uint32_t stage_tx_bytes;
   const float *scale, *bias;
@@ -429,6 +430,10 @@ k_conv3x3_tile(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                           ((int64_t)((h0 >> 1) + (lane >> 2)) * Wo + (x0 >> 1) + (lane & 3)) * (kC / 8) + q * 4;
             *reinterpret_cast<uint32_t *>(yw) = mine;
           }
+          if (a.y_bits && a.y_popcount) {     // density numerator of the next layer's input, from the ballot words
+            const int n = __reduce_add_sync(0xffffffffu, lane < 2 * RT ? __popc(mine) : 0);
+            if (lane == 0 && n) atomicAdd(a.y_popcount + (int64_t)b * a.T + t, n);
+          }
           if constexpr (COUNTS) {
             if (nspk) atomicAdd(a.counts + ((int64_t)b * a.T + t) * kC + c, nspk);
           }
@@ -584,6 +589,7 @@ int launch_conv3x3_tile(const snnqp_block_params &p, const uint8_t *x, const int
   a.tb_swapped = tb_swapped ? 1 : 0;
   a.one = 1;
   a.y_bits = p.y_format == SNNQP_SPIKES_BITS ? 1 : 0;
+  a.y_popcount = p.y_popcount;
   a.base_off_mode = 0;   // the hardware applies the 128B swizzle on absolute smem address bits (measured)
 #ifdef SNNQP_C1_BISECT
   static const int dbg_env = getenv("SNNQP_UMMA_DEBUG") ? atoi(getenv("SNNQP_UMMA_DEBUG")) : 0;   // bisection switches (tools/)

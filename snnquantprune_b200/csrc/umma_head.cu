@@ -573,6 +573,7 @@ bool umma_head_supported(const snnqp_block_params *p1, const snnqp_block_params 
     if (p2->x_format != SNNQP_SPIKES_BITS) return false;
   }
   if (p1 && p2 && p1->B > 0 && p2->B > 0 && p1->T != p2->T) return false;
+  if ((p1 && p1->B > 0 && p1->y_popcount) || (p2 && p2->B > 0 && p2->y_popcount)) return false;
   return true;
 }
 

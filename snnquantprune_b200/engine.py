@@ -70,7 +70,8 @@ class CextNetEngine:
   def __init__(self, packed: PackedCextNet, impl: int = _lib.IMPL_AUTO,
                tau: float = 2.0, v_threshold: float = 1.0, v_reset: float = 0.0,
                chunk: int = 296, device="cuda", lif_mode: int = _lib.LIF_FAST,
-               packed_spikes: Optional[bool] = None, fused_head: Optional[bool] = None):
+               packed_spikes: Optional[bool] = None, fused_head: Optional[bool] = None,
+               track_densities: bool = False):
     """``packed_spikes``: conv1 -> conv2 -> conv3 -> conv4 exchange bit-packed spikes (SNNQP_SPIKES_BITS, 8x fewer
     bytes; tcgen05 kernels only, the default unless impl == IMPL_SIMT).  ``lif_mode``: LIF_EXACT keeps the reference's
     op order in every block (bit-identical to the oracle); LIF_FAST (default) lets conv1 -- bound by its LIF
@@ -79,6 +80,9 @@ class CextNetEngine:
     self.pk = packed
     self.impl = impl
     self.lif_mode = lif_mode
+    # input densities of conv2 / conv3 / conv4 (the reference sows them, models.py:128-142) straight from the
+    # epilogues' ballot words (snnqp_block_params.y_popcount) instead of a separate pass over the tensors
+    self.track_densities = bool(track_densities)
     # the tcgen05 envelopes of conv1 .. conv4 (W = 128 / 64 / 32 / 16, 128 channels) = the reference geometry
     in_envelope = impl != _lib.IMPL_SIMT and packed.H == 128 and packed.channels == 128
     if packed_spikes and not in_envelope:
@@ -125,6 +129,8 @@ class CextNetEngine:
         "cnt5": torch.zeros((B, T, C), device=self.device, dtype=torch.int32),
         "d1": torch.empty((B, T, pk.dense1.cout), **u8),
         "d2": torch.empty((B, T, pk.dense2.cout), **u8),
+        # spikes emitted per (b, t) by conv1 / conv2 / conv3 (track_densities)
+        "dens": torch.zeros((3, B, T), device=self.device, dtype=torch.int32),
     }
     self._ws[key] = ws
     return ws
@@ -149,11 +155,13 @@ class CextNetEngine:
     return p
 
   # -- launches --------------------------------------------------------------
-  def _conv(self, i, x, y, B, Hin, Cin, pool, att=None, counts=None, collect=None, key=None):
+  def _conv(self, i, x, y, B, Hin, Cin, pool, att=None, counts=None, collect=None, key=None, popcount=None):
     L, P = _lib.lib(), _lib.ptr
     pk, C = self.pk, self.pk.channels
     lay = pk.convs[i]
     p = self._bp(B, Hin, Cin, C, x, y, pool, att, C)
+    if popcount is not None:
+      p.y_popcount = popcount.data_ptr()
     dump = u = None
     if collect is not None and key is not None:
       dt = torch.float32 if att is not None else torch.int32
@@ -197,6 +205,8 @@ class CextNetEngine:
     ws = self._workspace(B, Bc)
 
     # head: conv1 -> conv2 -> conv3, chunk by chunk
+    if self.track_densities:
+      ws["dens"].zero_()
     pipe = _HeadPipe(self, ws, collect)
     for b0 in range(0, B, Bc):
       n = min(Bc, B - b0)
@@ -210,9 +220,11 @@ class CextNetEngine:
       # instrumented pass: the generic epilogues (un-pooled spikes, membranes, accumulators) emit SNNQP_SPIKES_U8
       ws = self._u8_workspace(ws)
     s1, s2 = ws["s1"][:n], ws["s2"][:n]
-    self._conv(0, frames_chunk, s1, n, H, 2, 1, collect=collect, key="conv1")
-    self._conv(1, s1, s2, n, H // 2, C, 1, collect=collect, key="conv2")
-    self._conv(2, s2, ws["s3"][b0:b0 + n], n, H // 4, C, 1, collect=collect, key="conv3")
+    track = self.track_densities and self.packed_spikes and collect is None
+    dens = [ws["dens"][k, b0:b0 + n] if track else None for k in range(3)]
+    self._conv(0, frames_chunk, s1, n, H, 2, 1, collect=collect, key="conv1", popcount=dens[0])
+    self._conv(1, s1, s2, n, H // 2, C, 1, collect=collect, key="conv2", popcount=dens[1])
+    self._conv(2, s2, ws["s3"][b0:b0 + n], n, H // 4, C, 1, collect=collect, key="conv3", popcount=dens[2])
 
   def _u8_workspace(self, ws):
     if "u8" not in ws:
@@ -298,7 +310,13 @@ class CextNetEngine:
     if frames is not None:
       named = dict(conv_0_inpt=frames, **named)
     out = {}
+    tracked = {"conv_1_inpt": 0, "conv_2_inpt": 1, "conv_t_0_inpt": 2} if (self.track_densities and self.packed_spikes) else {}
     for k, x in named.items():
+      if k in tracked:
+        # counted by the producing epilogue (whole batch, not only the last head chunk)
+        frac = ws["dens"][tracked[k]].to(torch.float64) / float(x[0, 0].numel() * 8)
+        out[k] = {"min": float(frac.max()), "mean": float(frac.mean())}
+        continue
       d = density_stats(x, x.shape[0] * T, bits=self.packed_spikes and k in ("conv_1_inpt", "conv_2_inpt", "conv_t_0_inpt"))
       out[k] = {"min": float(d["min"]), "mean": float(d["mean"])}
     return out

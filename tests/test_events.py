@@ -113,7 +113,7 @@ def test_density_stats_bit_exact(cuda_lib, shape):
 def test_engine_densities_match_oracle(cuda_lib):
   """CextNetEngine.densities() == the reference's sowed input densities computed by the oracle on the same tensors."""
   from snnquantprune_b200 import CextNetEngine, pack_cextnet, synthetic
-  bits, T, H, B = 8, 4, 32, 3
+  bits, T, H, B = 8, 4, 128, 3          # the reference geometry: bit-packed spikes between conv1 .. conv4
   v = synthetic.make_variables(bits=bits, prune_percentage=0.5, T=T, H=H, seed=1)
   fr = torch.as_tensor(synthetic.make_frames(B, T, H, H, seed=2)).cuda()
   eng = CextNetEngine(pack_cextnet(v, bits, T, H, device="cuda"), lif_mode=0)
@@ -128,6 +128,13 @@ def test_engine_densities_match_oracle(cuda_lib):
     w = ref_events.sow_densities(np.swapaxes(x, 0, 1))             # (T, B, ...)
     assert abs(d[key]["min"] - w["min"]) < 1e-12 and abs(d[key]["mean"] - w["mean"]) < 1e-12, key
   assert 0.0 < d["conv_1_inpt"]["mean"] < 1.0
+  # the same densities counted by the producing epilogues (snnqp_block_params.y_popcount: popcount of the ballot words)
+  if eng.packed_spikes:
+    eng2 = CextNetEngine(pack_cextnet(v, bits, T, H, device="cuda"), lif_mode=0, track_densities=True)
+    eng2.forward(fr)
+    d2 = eng2.densities(fr)
+    for key in ("conv_1_inpt", "conv_2_inpt", "conv_t_0_inpt"):
+      assert abs(d2[key]["min"] - d[key]["min"]) < 1e-12 and abs(d2[key]["mean"] - d[key]["mean"]) < 1e-12, key
 
 
 # ---- committed golden fixture (tests/golden/make_golden.py: events_fixture) ---------------------------------------
