@@ -118,7 +118,9 @@ __device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {
 // LIFV (FAST only): 0 reference op order (FADD2 + FFMA2, FSET) | 1 single rounding fma(u, 0.5, v/2), FSET |
 // 2 single rounding, FFMA.SAT as the comparison (FMA pipe instead of the half-rate ALU pipe) | 3 single rounding,
 // FSET for quad positions 0-1 and FFMA.SAT for 2-3 (balances the two pipes).
-template <bool FAST, int kEpiWarps, int LIFV = 0>
+// POPC: also accumulate the per-(b, t) popcount of the emitted words (y_popcount); a separate instantiation because
+// even a never-taken branch in this issue-bound epilogue costs 6 % (measured, r2).
+template <bool FAST, int kEpiWarps, int LIFV = 0, bool POPC = false>
 __global__ void __launch_bounds__(threads_for(kEpiWarps), 1)
 k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
   constexpr int kThreads = threads_for(kEpiWarps);
@@ -361,7 +363,7 @@ k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
                 if (lane == i) mine = bal[i];
             }
             if (lane < NQ) *reinterpret_cast<uint32_t *>(yrow) = mine;
-            if (a.y_popcount) {          // density numerator of the next layer's input: popcount of the ballot words
+            if constexpr (POPC) {        // density numerator of the next layer's input: popcount of the ballot words
               const int n = __reduce_add_sync(0xffffffffu, lane < NQ ? __popc(mine) : 0);
               if (lane == 0 && n) atomicAdd(a.y_popcount + (int64_t)b * a.T + t, n);
             }
@@ -521,7 +523,16 @@ int launch_conv1_umma(const snnqp_block_params &p, const uint8_t *x, const int8_
     if (int rc = ensure_smem_attr<k_conv1_umma<true, 16, LV>>(kSmem)) return rc;                                   \
     k_conv1_umma<true, 16, LV><<<grid, threads_for(16), kSmem, st>>>(tmx, a);                                     \
   } while (0)
-  if (fast && (ew_env == 16 || a.y_bits)) {
+  if (a.y_popcount) {
+    if (!(fast && a.y_bits)) return unsupported("tcgen05 conv1: y_popcount needs the bit-packed production variant");
+    if (lifv == 0) {
+      if (int rc = ensure_smem_attr<k_conv1_umma<true, 16, 0, true>>(kSmem)) return rc;
+      k_conv1_umma<true, 16, 0, true><<<grid, threads_for(16), kSmem, st>>>(tmx, a);
+    } else {
+      if (int rc = ensure_smem_attr<k_conv1_umma<true, 16, 3, true>>(kSmem)) return rc;
+      k_conv1_umma<true, 16, 3, true><<<grid, threads_for(16), kSmem, st>>>(tmx, a);
+    }
+  } else if (fast && (ew_env == 16 || a.y_bits)) {
     if (lifv == 0) SNNQP_LAUNCH_C1(0);
     else if (lifv == 1) SNNQP_LAUNCH_C1(1);
     else if (lifv == 2) SNNQP_LAUNCH_C1(2);

@@ -94,7 +94,7 @@ struct UmmaArgs {
 
 // FAST: standard LIF constants (tau 2, threshold 1, reset 0), pooled output, no
 // instrumentation outputs -- the production variant; !FAST handles everything else.
-template <bool FAST, bool COUNTS, bool XBITS>
+template <bool FAST, bool COUNTS, bool XBITS, bool POPC = false>
 __global__ void __launch_bounds__(XBITS ? kThreadsX : kThreads, 1)
 k_conv3x3_tile(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                const UmmaArgs a) {
@@ -430,7 +430,7 @@ k_conv3x3_tile(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                           ((int64_t)((h0 >> 1) + (lane >> 2)) * Wo + (x0 >> 1) + (lane & 3)) * (kC / 8) + q * 4;
             *reinterpret_cast<uint32_t *>(yw) = mine;
           }
-          if (a.y_bits && a.y_popcount) {     // density numerator of the next layer's input, from the ballot words
+          if constexpr (POPC) {               // density numerator of the next layer's input, from the ballot words
             const int n = __reduce_add_sync(0xffffffffu, lane < 2 * RT ? __popc(mine) : 0);
             if (lane == 0 && n) atomicAdd(a.y_popcount + (int64_t)b * a.T + t, n);
           }
@@ -613,7 +613,13 @@ int launch_conv3x3_tile(const snnqp_block_params &p, const uint8_t *x, const int
     if (int rc = ensure_smem_attr<k_conv3x3_tile<FA, CO, XB>>(kSm)) return rc;                                 \
     k_conv3x3_tile<FA, CO, XB><<<grid, XB ? kThreadsX : kThreads, kSm, st>>>(tmx, tmw, a);                     \
   } while (0)
-  if (xbits) {
+  if (a.y_popcount) {
+    if (!(xbits && fast && a.y_bits && !counts))
+      return unsupported("tcgen05 conv: y_popcount needs bit-packed input and output, the production variant, no spike_counts");
+    constexpr int kSm = smem_bytes_for(7, kStagesBits, true);
+    if (int rc = ensure_smem_attr<k_conv3x3_tile<true, false, true, true>>(kSm)) return rc;
+    k_conv3x3_tile<true, false, true, true><<<grid, kThreadsX, kSm, st>>>(tmx, tmw, a);
+  } else if (xbits) {
     if (!fast) SNNQP_LAUNCH_TILE(false, false, true);
     else if (counts) SNNQP_LAUNCH_TILE(true, true, true);
     else SNNQP_LAUNCH_TILE(true, false, true);
