@@ -199,6 +199,17 @@ __host__ __device__ constexpr uint32_t make_idesc_i8(int M, int N, bool a_signed
                "r"(r[7])                                                                                \
                : "memory")
 
+// explicit shared-space 64-bit load / 128-bit store (a generic pointer derived from the dynamic smem base compiles to
+// LD.E / ST.E with address translation; the expander warps sit next to the MMA operand fetch on the same port)
+__device__ __forceinline__ uint2 lds64(uint32_t saddr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, const uint4 &v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // named barrier among a subset of warps (id 1..15; id 0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

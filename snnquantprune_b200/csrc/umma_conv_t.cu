@@ -296,8 +296,8 @@ k_conv3x3_tile(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           const uint32_t si = step % kStages, phi = (step / kStages) & 1;
           ptx::mbar_wait(pk_full + ps, pph);
           ptx::mbar_wait(in_empty + si, phi ^ 1);
-          const uint8_t *src = pk_smem + ps * kPkStageBytes;
-          uint8_t *dst = stage_smem + si * kStageBytes;
+          const uint32_t src = ptx::smem_u32(pk_smem + ps * kPkStageBytes);
+          const uint32_t dst = ptx::smem_u32(stage_smem + si * kStageBytes);
           // pass 1: this thread's packed words (<= kMaxTasks of them, kept in registers) and whether any bit is set
           constexpr int kMaxTasks = (ntask + 32 * kExpWarps - 1) / (32 * kExpWarps);
           uint2 pkd[kMaxTasks];
@@ -305,7 +305,7 @@ k_conv3x3_tile(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 #pragma unroll
           for (int i = 0; i < kMaxTasks; ++i) {
             const int task = et + i * 32 * kExpWarps;
-            pkd[i] = task < ntask ? *reinterpret_cast<const uint2 *>(src + (task >> 1) * 16 + (task & 1) * 8) : make_uint2(0u, 0u);
+            pkd[i] = task < ntask ? ptx::lds64(src + (task >> 1) * 16 + (task & 1) * 8) : make_uint2(0u, 0u);
             any |= pkd[i].x | pkd[i].y;
           }
           // per-warp verdict (no cross-warp barrier): the MMA issuer skips the step only if ALL expander warps saw
@@ -318,7 +318,7 @@ k_conv3x3_tile(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
               const int task = et + i * 32 * kExpWarps;
               if (task < ntask) {
                 const int r = task >> 1, hf = task & 1;
-                uint8_t *row = dst + r * 128;
+                const uint32_t row = dst + r * 128;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {                           // 16 channels = one 16-byte chunk
                   const uint32_t h16 = ((k & 2) ? pkd[i].y : pkd[i].x) >> ((k & 1) * 16);
@@ -327,7 +327,7 @@ k_conv3x3_tile(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                   o.y = (((h16 >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
                   o.z = (((h16 >> 8) & 0xFu) * 0x00204081u) & 0x01010101u;
                   o.w = (((h16 >> 12) & 0xFu) * 0x00204081u) & 0x01010101u;
-                  *reinterpret_cast<uint4 *>(row + ((((hf << 2) | k) ^ (r & 7)) << 4)) = o;
+                  ptx::sts128(row + ((((hf << 2) | k) ^ (r & 7)) << 4), o);
                 }
               }
             }
