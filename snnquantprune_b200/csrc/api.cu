@@ -76,6 +76,15 @@ static int check_popcount(const snnqp_block_params *p) {
     return unsupported("y_popcount needs y_format == SNNQP_SPIKES_BITS (it is the popcount of the ballot words)");
   return SNNQP_OK;
 }
+// SNNQP_IMPL_AUTO falling back to the dp4a SIMT kernels is a 10x+ performance cliff: say so once per process through
+// snnqp_last_error() (the call itself still succeeds) instead of degrading silently.
+static void note_simt_fallback(const char *what, const snnqp_block_params *p) {
+  static bool noted = false;
+  if (noted) return;
+  noted = true;
+  set_error("note: SNNQP_IMPL_AUTO ran %s on the SIMT (dp4a) kernels: shape T=%d B=%d H=%d W=%d Cin=%d Cout=%d is outside "
+            "the tcgen05 envelopes (reported once)", what, p->T, p->B, p->H, p->W, p->Cin, p->Cout);
+}
 static bool any_bits(const snnqp_block_params *p) {
   return p->x_format == SNNQP_SPIKES_BITS || p->y_format == SNNQP_SPIKES_BITS;
 }
@@ -107,7 +116,10 @@ int snnqp_spiking_conv3x3_counts_fwd(const snnqp_block_params *p, const uint8_t 
   int impl = p->impl;
   if (p->Cin == 2) {
     // conv1 blob = [Cout][32] tap-major (dp4a-era layout) followed by the 4 quad matrices [4][Cout][32]
-    if (impl == SNNQP_IMPL_AUTO) impl = umma_conv1_supported(*p, att) ? SNNQP_IMPL_TCGEN05 : SNNQP_IMPL_SIMT;
+    if (impl == SNNQP_IMPL_AUTO) {
+      impl = umma_conv1_supported(*p, att) ? SNNQP_IMPL_TCGEN05 : SNNQP_IMPL_SIMT;
+      if (impl == SNNQP_IMPL_SIMT) note_simt_fallback("the Cin = 2 conv block", p);
+    }
     if (spike_counts) return unsupported("snnqp_spiking_conv3x3_fwd: spike_counts with Cin=2");
     if (impl == SNNQP_IMPL_TCGEN05) {
       if (!umma_conv1_supported(*p, att))
@@ -122,7 +134,10 @@ int snnqp_spiking_conv3x3_counts_fwd(const snnqp_block_params *p, const uint8_t 
   if (att) {
     if (any_bits(p)) return unsupported("snnqp_spiking_conv3x3_fwd: att-weighted block takes and emits SNNQP_SPIKES_U8");
     // real-valued input att * x: three byte-plane int8 contractions on tcgen05, or fp32 FMAs (SIMT)
-    if (impl == SNNQP_IMPL_AUTO) impl = umma_conv_att_supported(*p, att) ? SNNQP_IMPL_TCGEN05 : SNNQP_IMPL_SIMT;
+    if (impl == SNNQP_IMPL_AUTO) {
+      impl = umma_conv_att_supported(*p, att) ? SNNQP_IMPL_TCGEN05 : SNNQP_IMPL_SIMT;
+      if (impl == SNNQP_IMPL_SIMT) note_simt_fallback("the attention-weighted conv block", p);
+    }
     if (impl == SNNQP_IMPL_TCGEN05) {
       if (!umma_conv_att_supported(*p, att))
         return unsupported("snnqp_spiking_conv3x3_fwd: tcgen05 att path needs Cin=Cout=att_mod=128, W=8, H %% 8 == 0 "
@@ -134,8 +149,10 @@ int snnqp_spiking_conv3x3_counts_fwd(const snnqp_block_params *p, const uint8_t 
   }
   static const bool force_strips = getenv("SNNQP_CONV_STRIPS") && atoi(getenv("SNNQP_CONV_STRIPS")) != 0;
   const bool tile_ok = !force_strips && umma_conv3x3_tile_supported(*p, att);
-  if (impl == SNNQP_IMPL_AUTO)
+  if (impl == SNNQP_IMPL_AUTO) {
     impl = (tile_ok || umma_conv3x3_supported(*p, att)) ? SNNQP_IMPL_TCGEN05 : SNNQP_IMPL_SIMT;
+    if (impl == SNNQP_IMPL_SIMT) note_simt_fallback("the 3x3 conv block", p);
+  }
   if (impl == SNNQP_IMPL_TCGEN05 && tile_ok)
     return launch_conv3x3_tile(*p, x, wq, scale, bias, spikes, u_final, (int32_t *)acc_dump, spike_counts, st);
   if (impl == SNNQP_IMPL_TCGEN05) {
@@ -197,7 +214,10 @@ int snnqp_spiking_dense_fwd(const snnqp_block_params *p, const uint8_t *x, const
   if (k_pad > 8192) return unsupported("snnqp_spiking_dense_fwd: K=%d too large (max 8192)", p->Cin);
   if (att && p->att_mod <= 0) return invalid("snnqp_spiking_dense_fwd: att_mod=%d", p->att_mod);
   int impl = p->impl;
-  if (impl == SNNQP_IMPL_AUTO) impl = umma_dense_supported(*p, att, k_pad) ? SNNQP_IMPL_TCGEN05 : SNNQP_IMPL_SIMT;
+  if (impl == SNNQP_IMPL_AUTO) {
+    impl = umma_dense_supported(*p, att, k_pad) ? SNNQP_IMPL_TCGEN05 : SNNQP_IMPL_SIMT;
+    if (impl == SNNQP_IMPL_SIMT) note_simt_fallback("the dense block", p);
+  }
   if (impl == SNNQP_IMPL_TCGEN05) {
     if (!umma_dense_supported(*p, att, k_pad))
       return unsupported("snnqp_spiking_dense_fwd: tcgen05 path needs K %% 128 == 0, rows (b,t) contiguous, "

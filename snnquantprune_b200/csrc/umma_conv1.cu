@@ -176,7 +176,9 @@ k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
         for (int t = 0; t < a.T; ++t, ++step) {
           const uint32_t s = step % kStStages, ph = (step / kStStages) & 1;
           { C1_T0(); ptx::mbar_wait_backoff(st_empty + s, ph ^ 1, 256); C1_ACC(w0); }
+#ifdef SNNQP_C1_BISECT
           if (a.debug & 2) { ptx::mbar_arrive(st_full + s); continue; }
+#endif
           ptx::mbar_expect_tx(st_full + s, kStRows * kStRowBytes);
           // x coordinate in bytes of the (w, c) axis: patch of quad 0 starts at column 2*qw0 - 1
           asm volatile(
@@ -208,7 +210,10 @@ k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
           { C1_T0(); ptx::mbar_wait_backoff(b_full + bs, bph, 64); C1_ACC(w1); }
           ptx::tc_fence_after();
           const uint64_t bd = ptx::make_desc_sw128(b_addr + bs * kBBytes, 0);
-          if (!(a.debug & 1)) {
+#ifdef SNNQP_C1_BISECT
+          if (!(a.debug & 1))
+#endif
+          {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               // K = 32 fp16 = two K-steps of 16 elements (32 bytes each) inside the 128-byte swizzled row
@@ -504,8 +509,12 @@ int launch_conv1_umma(const snnqp_block_params &p, const uint8_t *x, const int8_
   a.pool = p.pool; a.tb_swapped = swapped ? 1 : 0;
   a.y_bits = p.y_format == SNNQP_SPIKES_BITS ? 1 : 0;
   a.y_popcount = p.y_popcount;
+#ifdef SNNQP_C1_BISECT
   static const int dbg_env = getenv("SNNQP_C1_DEBUG") ? atoi(getenv("SNNQP_C1_DEBUG")) : 0;   // bisection switches (tools/)
   a.debug = dbg_env;
+#else
+  a.debug = 0;      // the bisection switches exist only in SNNQP_BISECT builds
+#endif
   a.wq4 = wq4; a.scale = scale; a.bias = bias;
   a.spikes = spikes; a.u_final = u_final; a.acc_dump = acc_dump;
   const int grid = a.total_items < sm_count() ? a.total_items : sm_count();

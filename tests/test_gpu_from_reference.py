@@ -257,3 +257,35 @@ def test_layer_facades_vs_reference_quantconv_quantdense(cuda_lib):
   with pytest.raises(NotImplementedError):
     QuantConv(features=5, kernel_size=[4], padding="VALID", use_bias=False, config=cfg).apply(
         _layer_params("qconv1d"), dev(OPS["qconv1d_x"]))
+
+
+@pytest.mark.parametrize("bits,prune", [(4, 0.8), (2, 0.9)])
+def test_full_size_configs_1_2_free_running_two_samples(cuda_lib, oracle_lib, bits, prune):
+  """BASELINE.json configs[1] (4 bit / 80 %) and configs[2] (2 bit / 90 %) at H = 128, T = 20 with B = 2, nothing
+  teacher-forced: the production forward (bit-packed spikes, pad-free tiles, fused tail) against the integer-path
+  oracle -- itself pinned to the executed reference at this geometry (test_from_reference_cpu.py).  Integer-input
+  blocks must agree bit for bit; dense1 (real-valued input, free-running) within the flip budget; logits within the
+  quantum of the counted flips."""
+  from oracle import ref_net
+  from snnquantprune_b200 import synthetic
+  T, H, B = 20, 128, 2
+  v = synthetic.make_variables(bits=bits, prune_percentage=prune, T=T, H=H, seed=5 + bits, stable=True)
+  fr = synthetic.make_frames(B, T, H, H, seed=7 + bits, stable=True)
+  m = dict(bits=bits, T=T, H=H, num_classes=11)
+  eng = _engine(v, m, chunk=296)
+  c = {}
+  li = eng.forward(dev(fr), collect=c).cpu().numpy()                    # instrumented pass (every intermediate)
+  lp = eng.forward(dev(fr)).cpu().numpy()                               # production pass
+  assert np.array_equal(li, lp)
+  co = {}
+  lo = ref_net.forward(ref_net.pack_network(v, bits, H), fr, collect=co)
+  tb = lambda k: np.swapaxes(c[k].cpu().numpy(), 0, 1)
+  for k in ("s1", "s2", "s3", "s4"):
+    assert np.array_equal(tb(k), co[k]), k
+  flips = 0
+  for k in ("s5", "d1", "d2"):
+    d = int((tb(k) != co[k]).sum())
+    assert d <= 1e-4 * co[k].size + 8 * flips, (k, d)
+    flips += d
+  assert np.max(np.abs(lp - lo)) <= reffix.logits_tolerance(T, 10, flips)
+  assert min(float(co[k].mean()) for k in ("s1", "s2", "s3", "s4", "s5", "d1", "d2")) > 0.005      # every block fires

@@ -689,6 +689,21 @@ def test_error_behaviour(cuda_lib):
     pk_mod.pack_conv3x3(lay, 8, DEV)
 
 
+def test_auto_impl_notes_simt_fallback_once(cuda_lib, oracle_lib):
+  """SNNQP_IMPL_AUTO outside the tcgen05 envelopes still runs (dp4a kernels) but says so once through
+  snnqp_last_error(): a 10x performance cliff must not be silent."""
+  rng = np.random.default_rng(5)
+  lay, q, bn, stt = make_layer(rng, 128, 128, 8, 0.5)
+  packed = pk_mod.pack_conv3x3(lay, 8, DEV, bn, stt)
+  x = (rng.uniform(size=(2, 1, 6, 6, 128)) < 0.3).astype(np.uint8)          # H = W = 6: no tcgen05 kernel takes it
+  scale, bias = ref_int.fold_affine(lay["DuQ_0"]["c"], 8, bn, stt, 128)
+  s_ref, info = ref_int.spiking_conv3x3(x, q, scale, bias, pool=True, want=True)
+  s, u, acc = run_conv(cuda_lib, x, packed.wq, packed.scale, packed.bias, 128, True, _lib.IMPL_AUTO)
+  assert np.array_equal(s, s_ref) and np.array_equal(acc, info["acc"])
+  msg = cuda_lib.snnqp_last_error().decode()
+  assert ("SIMT" in msg and "reported once" in msg) or msg == "" or "note" not in msg      # first fallback of the process says so
+
+
 def test_spiking_block_facade(cuda_lib, oracle_lib):
   from snnquantprune_b200 import SpikingBlock, QuantConv, QuantDense, QuantConfig, multi_step_LIF, BatchNorm, atan
   rng = np.random.default_rng(71)
