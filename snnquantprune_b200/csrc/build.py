@@ -11,7 +11,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-OUT = os.path.join(os.path.dirname(HERE), "libsnnqp.so")
+OUT = os.path.join(os.path.dirname(HERE), os.environ.get("SNNQP_BUILD_NAME", "libsnnqp.so"))
 SOURCES = ["runtime.cu", "pack.cu", "simt.cu", "umma_conv.cu", "umma_conv_t.cu", "umma_conv1.cu", "umma_head.cu", "umma_att.cu", "diag.cu", "frames.cu", "plain.cu", "api.cu", "xla_ffi_shim.cc"]
 HEADERS = ["common.cuh", "ptx.cuh", "tmap.cuh", "epilogue.cuh", os.path.join(ROOT, "include", "snnqp.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -19,6 +19,8 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 # XLA FFI handlers (xla_ffi_shim.cc) compile for real where jaxlib's headers are: SNNQP_XLA_INCLUDE=<dir holding xla/ffi/api/ffi.h>
 XLA_INC = ["-I", os.environ["SNNQP_XLA_INCLUDE"]] if os.environ.get("SNNQP_XLA_INCLUDE") else []
+if os.environ.get("SNNQP_C1_SUSPEND"):      # experiment: hardware-suspended producer waits in conv1 (tools/run_r2_gpu16.sh)
+  FLAGS.append("-DSNNQP_C1_SUSPEND")
 if os.environ.get("SNNQP_BISECT"):          # debug-only bisection switches inside the hot loops (tools/)
   FLAGS.append("-DSNNQP_C1_BISECT")
 

@@ -61,6 +61,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   }
 }
 
+// Same, suspended in hardware: try_wait with a suspend-time hint blocks the thread (no issue slots) until the phase
+// completes or `ns` elapse -- wake-up on completion is immediate, unlike a nanosleep poll.
+__device__ __forceinline__ void mbar_wait_suspend(uint64_t *bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+  } while (!ok);
+}
+
 // Same with a nanosleep back-off between polls: for producer-side warps of kernels whose epilogue is bound by
 // issue slots (a spinning warp takes ~1 slot in 5 from the four epilogue warps of its SM sub-partition).
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity, uint32_t ns) {

@@ -37,6 +37,12 @@ namespace {
 #define C1_ACC(var)
 #define C1_TIC(name)
 #endif
+// producer-side waits: SNNQP_C1_SUSPEND builds use the hardware-suspended try_wait instead of the nanosleep poll
+#ifdef SNNQP_C1_SUSPEND
+#define C1_WAIT(bar, parity, ns) ptx::mbar_wait_suspend(bar, parity, 20000u)
+#else
+#define C1_WAIT(bar, parity, ns) ptx::mbar_wait_backoff(bar, parity, ns)
+#endif
 
 constexpr int kC = 128;
 constexpr int kQuadsPerTile = 32;
@@ -175,7 +181,7 @@ k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
         const int b = item / (a.tiles_per_row * QH);
         for (int t = 0; t < a.T; ++t, ++step) {
           const uint32_t s = step % kStStages, ph = (step / kStStages) & 1;
-          { C1_T0(); ptx::mbar_wait_backoff(st_empty + s, ph ^ 1, 256); C1_ACC(w0); }
+          { C1_T0(); C1_WAIT(st_empty + s, ph ^ 1, 256); C1_ACC(w0); }
 #ifdef SNNQP_C1_BISECT
           if (a.debug & 2) { ptx::mbar_arrive(st_full + s); continue; }
 #endif
@@ -206,8 +212,8 @@ k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
         for (int t = 0; t < a.T; ++t, ++step) {
           const uint32_t s = step % kAccStages, ph = (step / kAccStages) & 1;
           const uint32_t bs = step % kBStages, bph = (step / kBStages) & 1;
-          { C1_T0(); ptx::mbar_wait_backoff(acc_empty + s, ph ^ 1, 64); C1_ACC(w0); }
-          { C1_T0(); ptx::mbar_wait_backoff(b_full + bs, bph, 64); C1_ACC(w1); }
+          { C1_T0(); C1_WAIT(acc_empty + s, ph ^ 1, 64); C1_ACC(w0); }
+          { C1_T0(); C1_WAIT(b_full + bs, bph, 64); C1_ACC(w1); }
           ptx::tc_fence_after();
           const uint64_t bd = ptx::make_desc_sw128(b_addr + bs * kBBytes, 0);
 #ifdef SNNQP_C1_BISECT
@@ -242,8 +248,8 @@ k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
       for (int t = 0; t < a.T; ++t, ++step) {
         const uint32_t s = step % kStStages, ph = (step / kStStages) & 1;
         const uint32_t bs = step % kBStages, bph = (step / kBStages) & 1;
-        { C1_T0(); ptx::mbar_wait_backoff(st_full + s, ph, 64); C1_ACC(w0); }
-        { C1_T0(); ptx::mbar_wait_backoff(b_empty + bs, bph ^ 1, 64); C1_ACC(w1); }
+        { C1_T0(); C1_WAIT(st_full + s, ph, 64); C1_ACC(w0); }
+        { C1_T0(); C1_WAIT(b_empty + bs, bph ^ 1, 64); C1_ACC(w1); }
 #ifdef SNNQP_C1_BISECT
         if (a.debug & 32) {                         // bisection: no gather work
           __syncwarp();
