@@ -21,6 +21,8 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
 XLA_INC = ["-I", os.environ["SNNQP_XLA_INCLUDE"]] if os.environ.get("SNNQP_XLA_INCLUDE") else []
 if os.environ.get("SNNQP_C1_SUSPEND"):      # experiment: hardware-suspended producer waits in conv1 (tools/run_r2_gpu16.sh)
   FLAGS.append("-DSNNQP_C1_SUSPEND")
+if os.environ.get("SNNQP_EXP_WARPS"):       # experiment: number of expander warps of the bit-packed tile kernel
+  FLAGS.append("-DSNNQP_EXP_WARPS=" + os.environ["SNNQP_EXP_WARPS"])
 if os.environ.get("SNNQP_BISECT"):          # debug-only bisection switches inside the hot loops (tools/)
   FLAGS.append("-DSNNQP_C1_BISECT")
 

@@ -54,7 +54,10 @@ constexpr int kColsPerThread = kRowsPerThread * kTileW;      // 32 accumulator c
 constexpr int kThreads = (kEpiWarps + 2) * 32;  // + TMA warp + MMA warp
 // Bit-packed input (SNNQP_SPIKES_BITS): TMA stages the packed tile (16 B per position), two expander warps turn
 // bits into the u8 K-major 128B-swizzled MMA operand (3 integer ops per 4 bytes: nibble * 0x00204081 & 0x01010101).
-constexpr int kExpWarps = 4;
+#ifndef SNNQP_EXP_WARPS
+#define SNNQP_EXP_WARPS 3
+#endif
+constexpr int kExpWarps = SNNQP_EXP_WARPS;   // 3 keeps the MMA issuer's SM sub-partition free of an expander warp (A/B: tools/run_r2_gpu17.sh)
 constexpr int kThreadsX = kThreads + kExpWarps * 32;
 constexpr int kPkStages = 6, kPkStageBytes = 2944;   // >= 180 * 16 B, 128-aligned
 constexpr int kTmemCols = 512;
