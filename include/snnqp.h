@@ -157,6 +157,14 @@ typedef struct snnqp_block_params {
  *          1e-5), spikes may flip only when un is within an ulp of 1. */
 #define SNNQP_LIF_EXACT 0
 #define SNNQP_LIF_FAST 1
+/*   TENSOR (conv1, tcgen05 path, production variant only; EXACT elsewhere): the
+ *          leak runs on the tensor core -- tcgen05.mma's scale-input-d computes
+ *          D = A * B + D / 2, so the TMEM accumulator IS the membrane (scale
+ *          folded into three bf16 weight pieces, bias on a constant-one K
+ *          column) and the epilogue only compares, resets and packs.  The
+ *          accumulation rounding is the tensor core's, not IEEE fma: tolerance
+ *          parity (membrane 1e-5, spike flips <= 1e-4), not bit parity. */
+#define SNNQP_LIF_TENSOR 2
 
 /* SpikingBlock(QuantConv 3x3 pad 1, BatchNorm, multi_step_LIF) over T steps
  * with zero initial carry (spiking_learning.py:441-472), optionally followed

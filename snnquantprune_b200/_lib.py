@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("SNNQP_LIB") or os.path.join(_HERE, "libsnnqp.so")
 ABI_VERSION = 3          # include/snnqp.h SNNQP_ABI_VERSION (block params carry x_format / y_format / lif_mode)
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
 SPIKES_U8, SPIKES_BITS = 0, 1
-LIF_EXACT, LIF_FAST = 0, 1
+LIF_EXACT, LIF_FAST, LIF_TENSOR = 0, 1, 2
 
 
 class SnnqpError(RuntimeError):

@@ -67,7 +67,7 @@ static int check_conv(const snnqp_block_params *p, const void *x, const void *wq
   if ((unsigned)p->x_format > SNNQP_SPIKES_BITS || (unsigned)p->y_format > SNNQP_SPIKES_BITS)
     return invalid("%s: x_format=%d y_format=%d (SNNQP_SPIKES_U8 / SNNQP_SPIKES_BITS)", fn, p->x_format, p->y_format);
   // 101..103: developer selection of one single-rounding variant (tests / tools); SNNQP_LIF_FAST = the library's pick
-  if ((unsigned)p->lif_mode > SNNQP_LIF_FAST && !(p->lif_mode >= 101 && p->lif_mode <= 103))
+  if ((unsigned)p->lif_mode > SNNQP_LIF_TENSOR && !(p->lif_mode >= 101 && p->lif_mode <= 103))
     return invalid("%s: lif_mode=%d", fn, p->lif_mode);
   return SNNQP_OK;
 }

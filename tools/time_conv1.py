@@ -1,6 +1,7 @@
 """GPU timing of the conv1 fused block alone.  python tools/time_conv1.py [B] [iters]
 Runs every (output layout, LIF variant) combination: u8 / bit-packed spikes x reference-order LIF (0) and the
-single-rounding variants (lif_mode 101 FSET, 102 FFMA.SAT, 103 mixed = SNNQP_LIF_FAST)."""
+single-rounding variants (lif_mode 101 FSET, 102 FFMA.SAT, 103 mixed = SNNQP_LIF_FAST) and 2 = SNNQP_LIF_TENSOR (leak on the
+tensor core).  SNNQP_C1_MODES=0,103,2 restricts the list."""
 import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
@@ -11,8 +12,9 @@ T, H, C = 20, 128, 128
 v = synthetic.make_variables(bits=8, prune_percentage=0.5, T=T, H=H, seed=1)
 fr = torch.as_tensor(synthetic.make_frames(B, T, H, H, seed=0), device="cuda")
 ref = None
+MODES = [int(x) for x in os.environ.get('SNNQP_C1_MODES', '0,101,102,103,2').split(',')]
 for bits in (False, True):
-  for lm in (0, 101, 102, 103):
+  for lm in MODES:
     eng = CextNetEngine(pack_cextnet(v, 8, T, H), chunk=B, lif_mode=lm, packed_spikes=bits)
     s1 = eng._workspace(B, B)["s1"][:B]
     fn = lambda: eng._conv(0, fr, s1, B, H, 2, 1)
