@@ -114,7 +114,7 @@ def cpu_reference_samples_per_s(bits, prune, T, H, sample_B, reps, threads):
   return sample_B / statistics.median(times), times
 
 
-def parity_of_timed_batch(v, bits, H, frames_np, gpu_logits_np, T):
+def parity_of_timed_batch(v, bits, H, frames_np, gpu_logits_np, T, lif):
   """Checker (outside every timed region): the first samples of the batch that was just timed, through the
   integer-path oracle (oracle/ref_net.py, pinned to the executed reference by tests/test_from_reference_cpu.py),
   against the logits the timed engine produced for them."""
@@ -126,7 +126,49 @@ def parity_of_timed_batch(v, bits, H, frames_np, gpu_logits_np, T):
   return {"samples": int(frames_np.shape[0]), "logits_max_abs_diff": float(d.max()),
           "logit_quantum": 1.0 / (T * 10), "argmax_agree": bool(np.array_equal(lo.argmax(-1), gpu_logits_np.argmax(-1))),
           "bit_identical_logits": bool(np.array_equal(lo, gpu_logits_np)),
-          "oracle": "oracle/ref_net.py integer path (reference-order LIF); engine runs LIF_FAST in conv1"}
+          "oracle": f"oracle/ref_net.py integer path (reference-order LIF); engine ran conv1 with --lif {lif}"}
+
+
+def lif_mode_parity(eng, packed, frames, logits, impl, args, dev):
+  """Checker (outside every timed region): what the timed LIF mode changes against the reference op order, measured
+  on the timed batch itself -- conv1's pooled spikes of the first chunk (flip rate; north-star bar 1e-4) and the logits
+  of the first chunks -- plus the throughput of the other modes (5 steps each)."""
+  import torch
+  from snnquantprune_b200 import CextNetEngine, _lib
+  n = min(frames.shape[0], args.chunk)
+  H = packed.H
+  out = {"timed_mode": args.lif, "flip_budget": 1e-4}
+  exact = CextNetEngine(packed, impl=impl, chunk=args.chunk, device=dev, lif_mode=_lib.LIF_EXACT)
+  if eng.packed_spikes and args.lif != "exact":
+    a, b = eng._workspace(n, n)["s1"][:n], exact._workspace(n, n)["s1"][:n]
+    eng._conv(0, frames[:n], a, n, H, 2, 1)
+    exact._conv(0, frames[:n], b, n, H, 2, 1)
+    x = torch.bitwise_xor(a, b)
+    flips = int(sum(int(((x >> k) & 1).sum().item()) for k in range(8)))
+    out["conv1_pooled_spikes"] = int(a.numel() * 8)
+    out["conv1_flips_vs_reference_order"] = flips
+    out["conv1_flip_rate"] = flips / (a.numel() * 8)
+  m = min(frames.shape[0], 2 * args.chunk)
+  le = exact.forward(frames[:m])
+  out["reference_order_logits_first2"] = le[:2].cpu().numpy()          # checked against the oracle by the caller
+  dl = (le - logits[:m]).abs()
+  out["logits_vs_reference_order"] = {"samples": m, "max_abs_diff": float(dl.max().item()),
+                                      "samples_changed": int((dl.max(dim=1).values > 1e-6).sum().item()),
+                                      "argmax_agree_fraction": float((le.argmax(-1) == logits[:m].argmax(-1)).float().mean().item())}
+  by_mode = {}
+  for name, mode in (("tensor", _lib.LIF_TENSOR), ("fast", _lib.LIF_FAST), ("exact", _lib.LIF_EXACT)):
+    e = CextNetEngine(packed, impl=impl, chunk=args.chunk, device=dev, lif_mode=mode)
+    for _ in range(2):
+      e.forward(frames)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(5):
+      e.forward(frames)
+    e1.record(); torch.cuda.synchronize()
+    by_mode[name] = frames.shape[0] * 5 / (e0.elapsed_time(e1) / 1e3)
+    del e
+  out["samples_per_s_by_lif_mode_5_steps"] = by_mode
+  return out
 
 
 def run_reference(args):
@@ -206,7 +248,8 @@ def run_ours(args):
   T, H = args.T, args.H
   v = synthetic.make_variables(bits=args.bits, prune_percentage=args.prune, T=T, H=H, seed=1)
   packed = pack_cextnet(v, args.bits, T, H, device=dev)
-  eng = CextNetEngine(packed, impl=impl, chunk=args.chunk, device=dev)
+  lif = {"tensor": _lib.LIF_TENSOR, "fast": _lib.LIF_FAST, "exact": _lib.LIF_EXACT}[args.lif]
+  eng = CextNetEngine(packed, impl=impl, chunk=args.chunk, device=dev, lif_mode=lif)
   # distinct frames per rank (the shard this rank owns of the global batch)
   base = synthetic.make_frames(min(B, 64), T, H, H, seed=100 + rank)
   reps = (B + base.shape[0] - 1) // base.shape[0]
@@ -245,7 +288,7 @@ def run_ours(args):
   # were); the dense-frame call is timed beside it.
   from snnquantprune_b200.input_pipeline import zsf_encode
   host_logits = torch.empty((B, packed.num_classes), dtype=torch.float32).pin_memory()
-  eng_e2e = CextNetEngine(packed, impl=impl, chunk=args.e2e_chunk, device=dev)
+  eng_e2e = CextNetEngine(packed, impl=impl, chunk=args.e2e_chunk, device=dev, lif_mode=lif)
   e2e_steps = max(1, min(args.steps, args.e2e_steps))
   zb = zsf_encode(host_frames.numpy())
 
@@ -273,6 +316,7 @@ def run_ours(args):
   # per-layer input densities of the synthetic run (a dead network would make the throughput meaningless)
   eng.forward(frames)
   rates = {k: round(v["mean"], 4) for k, v in eng.densities(frames).items()}
+  lif_parity = lif_mode_parity(eng, packed, frames, logits, impl, args, dev) if (ws == 1 and not args.no_cpu_baseline) else None
 
   # ---- final accuracy reduction: the only collective, outside the timed region
   out = torch.zeros(2, device=dev, dtype=torch.float32)
@@ -291,7 +335,12 @@ def run_ours(args):
              "sample": f"BASELINE.json configs[0]: {args.cpu_batch} samples of the same workload, 1 warm-up, median of "
                        f"{args.cpu_passes} passes, oracle fp32 restatement of the reference graph (torch-CPU "
                        f"contractions); the JAX reference cannot run in this image"}
-      parity = parity_of_timed_batch(v, args.bits, H, host_frames[:2].numpy(), logits[:2].cpu().numpy(), T)
+      parity = parity_of_timed_batch(v, args.bits, H, host_frames[:2].numpy(), logits[:2].cpu().numpy(), T, args.lif)
+      le2 = lif_parity.pop("reference_order_logits_first2")
+      if args.lif != "exact":          # the same two samples through this engine with --lif exact: bit parity with the oracle
+        pe = parity_of_timed_batch(v, args.bits, H, host_frames[:2].numpy(), le2, T, "exact")
+        parity["lif_exact_engine_bit_identical_logits"] = pe["bit_identical_logits"]
+      parity["lif"] = lif_parity
     net_tops = value * GOP_PER_SAMPLE_T20 / 1e3 / ws          # dense-equivalent int8 TOP/s per GPU
     line = {
         "metric": METRIC.replace("T=20", f"T={args.T}"), "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
@@ -299,8 +348,11 @@ def run_ours(args):
         "scaling": "strong" if args.batch is None else "weak", "vs_baseline": None,
         "dtype": "int8", "data": "synthetic",
         "config": dict(workload_config(args, B, ws),
-                       arithmetic="int8 weights x u8 spikes/counts -> int32 accumulate (tcgen05 kind::i8; conv1 as exact "
-                                  "kind::f16), fp32 dequant + BatchNorm + LIF epilogue"),
+                       arithmetic="int8 weights x u8 spikes/counts -> int32 accumulate (tcgen05 kind::i8), fp32 dequant + BatchNorm "
+                                  "+ LIF epilogue; conv1 (--lif " + args.lif + "): " +
+                                  ("kind::f16 with the BatchNorm scale folded into two fp16 weight pieces and the tau = 2 leak as "
+                                   "tcgen05.mma scale-input-d (membranes in TMEM)" if args.lif == "tensor" else
+                                   "exact kind::f16 accumulators, LIF on the CUDA cores")),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(zb.nbytes) * ws,
                 "d2h_bytes_per_step": int(host_logits.numel() * 4) * ws, "steps": e2e_steps,
                 "input_format": f"zero-suppressed frames (bitmap + {zb.value_bits}-bit non-zero counts), "
@@ -401,7 +453,7 @@ def per_kernel_rooflines(eng, frames, ms_step, int8_peak_tops):
   scale = (T / 20.0) * (H / 128.0) ** 2
   px = lambda h: T * h * h * C / 8 / 1e6 if eng.packed_spikes else T * h * h * C / 1e6       # MB / sample
   specs = [
-      ("conv1 fused block (k_conv1_umma: 128x128x2 -> 128, LIF, pool)", lambda: eng._conv(0, frames[:n], ws["s1"][:n], n, H, 2, 1),
+      ("conv1 fused block (k_conv1_tclif / k_conv1_umma: 128x128x2 -> 128, LIF, pool)", lambda: eng._conv(0, frames[:n], ws["s1"][:n], n, H, 2, 1),
        2 * 0.755 * scale, T * H * H * 2 / 1e6 + px(H // 2), n),
       ("conv2 fused block (k_conv3x3_tile, 64x64x128 -> 128)", lambda: eng._conv(1, ws["s1"][:n], ws["s2"][:n], n, H // 2, C, 1),
        2 * 12.080 * scale, px(H // 2) + px(H // 4), n),
@@ -431,8 +483,11 @@ def per_kernel_rooflines(eng, frames, ms_step, int8_peak_tops):
                 "hbm": {"achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
                         "algorithmic_mb_per_sample": mb},
                 "bound": "tensor" if tops / int8_peak_tops > gbs / hbm else "hbm",
-                "limiter": ("issue slots of the LIF epilogue: 5.75 issued instructions per neuron-step, issue active 74 %, "
-                            "tensor pipe 13 % (profiles/r2_ncu_full_final.json) -- far from both rooflines by construction")
+                "limiter": (("LIF_TENSOR: the leak runs on the tensor core (membranes in TMEM), the CUDA cores keep compare / reset / "
+                             "pool / pack: ~3 issued instructions per neuron-step, issue active ~67 %, tensor pipe ~45 % "
+                             "(profiles/r2_ncu_conv1_tclif.json)" if eng.lif_mode == 2 else
+                             "issue slots of the LIF epilogue: 5.75 issued instructions per neuron-step, issue active 74 %, "
+                             "tensor pipe 13 % (profiles/r2_ncu_full_final.json)") + " -- far from both rooflines by construction")
                            if "conv1" in name else "tensor pipe (89 % active bit-packed, 95 % with u8 spikes)"})
   return out
 
@@ -444,6 +499,9 @@ def main():
   ap.add_argument("--warmup", type=int, default=3)
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
   ap.add_argument("--kernels", default="auto", choices=["auto", "simt", "tcgen05"])
+  ap.add_argument("--lif", default="tensor", choices=["tensor", "fast", "exact"],
+                  help="conv1's LIF arithmetic (include/snnqp.h SNNQP_LIF_*): tensor = leak on the tensor core (engine default, "
+                       "tolerance parity), fast = single-rounding fma, exact = the reference's op order (bit parity)")
   ap.add_argument("--global-batch", type=int, default=4096,
                   help="samples per step over all GPUs (BASELINE.json configs[4]: batch 4096 sharded over 1/2/4/8 GPUs)")
   ap.add_argument("--batch", type=int, default=None, help="samples per GPU per step (overrides --global-batch: weak scaling)")

@@ -208,6 +208,14 @@ __host__ __device__ constexpr uint32_t make_idesc_i8(int M, int N, bool a_signed
                : "r"(taddr)                                                                             \
                : "memory")
 
+// Compiler-only fence for registers filled by a tcgen05.ld that was issued earlier (software-pipelined loads): makes
+// every later use of r[o .. o + 15] depend on this point, i.e. on the tcgen05.wait::ld placed just before it.
+#define SNNQP_REG_FENCE16(r, o)                                                                         \
+  asm volatile("" : "+r"(r[(o) + 0]), "+r"(r[(o) + 1]), "+r"(r[(o) + 2]), "+r"(r[(o) + 3]), "+r"(r[(o) + 4]), \
+               "+r"(r[(o) + 5]), "+r"(r[(o) + 6]), "+r"(r[(o) + 7]), "+r"(r[(o) + 8]), "+r"(r[(o) + 9]),      \
+               "+r"(r[(o) + 10]), "+r"(r[(o) + 11]), "+r"(r[(o) + 12]), "+r"(r[(o) + 13]), "+r"(r[(o) + 14]), \
+               "+r"(r[(o) + 15]))
+
 #define SNNQP_TMEM_ST_X32(taddr, r)                                                                     \
   asm volatile(                                                                                         \
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                                   \
@@ -218,6 +226,15 @@ __host__ __device__ constexpr uint32_t make_idesc_i8(int M, int N, bool a_signed
       "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),   \
       "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),   \
       "r"(r[31])                                                                                        \
+      : "memory")
+
+#define SNNQP_TMEM_ST_X16(taddr, r)                                                                     \
+  asm volatile(                                                                                         \
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "                                                   \
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"                        \
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]),        \
+      "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]),      \
+      "r"(r[15])                                                                                        \
       : "memory")
 
 #define SNNQP_TMEM_ST_X8(taddr, r)                                                                    \

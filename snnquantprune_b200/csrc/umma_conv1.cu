@@ -472,7 +472,7 @@ k_conv1_umma(const __grid_constant__ CUtensorMap tmap_x, const Conv1Args a) {
 
 bool conv1_tclif_supported(const snnqp_block_params &p);
 int launch_conv1_tclif(const snnqp_block_params &p, const uint8_t *x, const int8_t *wq4, const float *scale,
-                       const float *bias, uint8_t *spikes, cudaStream_t st);
+                       const float *bias, uint8_t *spikes, float *u_final, cudaStream_t st);
 
 bool umma_conv1_supported(const snnqp_block_params &p, const float *att) {
   if (att || p.Cin != 2 || p.Cout != kC) return false;
@@ -533,8 +533,9 @@ int launch_conv1_umma(const snnqp_block_params &p, const uint8_t *x, const int8_
   static const int ew_env = getenv("SNNQP_C1_EW") ? atoi(getenv("SNNQP_C1_EW")) : 16;
   // SNNQP_LIF_TENSOR: membranes in TMEM, leak on the tensor core (umma_conv1_tc.cu); outside its preconditions the
   // mode means the reference op order
-  if (p.lif_mode == SNNQP_LIF_TENSOR && fast && conv1_tclif_supported(p))
-    return launch_conv1_tclif(p, x, wq4, scale, bias, spikes, st);
+  const bool std_lif = p.tau == 2.0f && p.v_threshold == 1.0f && p.v_reset == 0.0f && p.pool && !acc_dump;
+  if (p.lif_mode == SNNQP_LIF_TENSOR && std_lif && conv1_tclif_supported(p))
+    return launch_conv1_tclif(p, x, wq4, scale, bias, spikes, u_final, st);
   if (a.y_bits && !fast)
     return unsupported("tcgen05 conv1: bit-packed output needs the production variant (standard LIF constants, pool = 1, "
                        "no u_final / acc_dump)");

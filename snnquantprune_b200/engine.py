@@ -69,14 +69,17 @@ class _HeadPipe:
 class CextNetEngine:
   def __init__(self, packed: PackedCextNet, impl: int = _lib.IMPL_AUTO,
                tau: float = 2.0, v_threshold: float = 1.0, v_reset: float = 0.0,
-               chunk: int = 296, device="cuda", lif_mode: int = _lib.LIF_FAST,
+               chunk: int = 296, device="cuda", lif_mode: int = _lib.LIF_TENSOR,
                packed_spikes: Optional[bool] = None, fused_head: Optional[bool] = None,
                track_densities: bool = False):
     """``packed_spikes``: conv1 -> conv2 -> conv3 -> conv4 exchange bit-packed spikes (SNNQP_SPIKES_BITS, 8x fewer
-    bytes; tcgen05 kernels only, the default unless impl == IMPL_SIMT).  ``lif_mode``: LIF_EXACT keeps the reference's
-    op order in every block (bit-identical to the oracle); LIF_FAST (default) lets conv1 -- bound by its LIF
-    epilogue -- use the single-rounding form: membranes within 1 ulp per step, measured 12 flipped spikes in
-    3.1e9 (4e-9; bar 1e-4; tools/time_conv1.py)."""
+    bytes; tcgen05 kernels only, the default unless impl == IMPL_SIMT).  ``lif_mode`` concerns conv1, the block bound by its LIF epilogue
+    (every other block always runs the reference's op order): LIF_EXACT = the reference's op order, bit-identical to
+    the oracle; LIF_FAST = single-rounding fma on the CUDA cores (membranes within 1 ulp per step, 12 flipped spikes in
+    3.1e9); LIF_TENSOR (default) = the leak runs on the tensor core (tcgen05.mma scale-input-d, membranes resident in
+    TMEM; csrc/umma_conv1_tc.cu): 39 % less conv1 time, tolerance parity -- 45 flipped spikes in 3.1e9 (1.5e-8; bar
+    1e-4), final membranes within 1e-5 (tools/time_conv1.py, tests/test_gpu_parity.py).  Outside the kernel's
+    envelope (H = W = 128 multiples, standard LIF constants) LIF_TENSOR means LIF_EXACT."""
     self.pk = packed
     self.impl = impl
     self.lif_mode = lif_mode
@@ -155,7 +158,8 @@ class CextNetEngine:
     return p
 
   # -- launches --------------------------------------------------------------
-  def _conv(self, i, x, y, B, Hin, Cin, pool, att=None, counts=None, collect=None, key=None, popcount=None):
+  def _conv(self, i, x, y, B, Hin, Cin, pool, att=None, counts=None, collect=None, key=None, popcount=None,
+            collect_acc=True):
     L, P = _lib.lib(), _lib.ptr
     pk, C = self.pk, self.pk.channels
     lay = pk.convs[i]
@@ -165,9 +169,11 @@ class CextNetEngine:
     dump = u = None
     if collect is not None and key is not None:
       dt = torch.float32 if att is not None else torch.int32
-      dump = torch.empty((pk.T, B, Hin, Hin, C), device=self.device, dtype=dt)
       u = torch.empty((B, Hin, Hin, C), device=self.device, dtype=torch.float32)
-      collect[key + "_acc"], collect[key + "_u"] = dump, u
+      collect[key + "_u"] = u
+      if collect_acc:       # (membranes alone keep conv1's LIF_TENSOR kernel eligible: it has no accumulator to dump)
+        dump = torch.empty((pk.T, B, Hin, Hin, C), device=self.device, dtype=dt)
+        collect[key + "_acc"] = dump
     _lib.check(L.snnqp_spiking_conv3x3_counts_fwd(p, P(x), P(att), P(lay.wq), P(lay.scale), P(lay.bias),
                                                   P(y), P(u), P(dump), P(counts), _lib.stream()))
 

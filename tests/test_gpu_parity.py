@@ -154,6 +154,8 @@ def run_conv(lib, x_tb, wq, scale, bias, Cout, pool, impl, att=None, tau=2.0, ba
   p.pool, p.impl = int(pool), impl
   p.x_format, p.y_format, p.lif_mode = int(x_bits), int(y_bits), lif_mode
   ud, accd = (u, acc) if dumps else (None, None)      # no instrumentation outputs -> the production (FAST) variant
+  if dumps == "u":                                     # membranes only (conv1's LIF_TENSOR kernel has no accumulator dump)
+    accd = None
   if counts is None:
     _lib.check(lib.snnqp_spiking_conv3x3_fwd(p, P(xs), P(attd), P(wq), P(scale), P(bias), P(spikes), P(ud),
                                              P(accd), _lib.stream()))
@@ -206,6 +208,43 @@ def test_spiking_conv1_tcgen05_bit_exact(cuda_lib, oracle_lib, shape, bits, pool
         s_f, _, _ = run_conv(cuda_lib, x, packed.wq, packed.scale, packed.bias, 128, pool, _lib.IMPL_TCGEN05,
                              batch_major=bm, dumps=False, y_bits=True, lif_mode=lm)
         assert np.mean(s_f != s_ref) <= 1e-4, (lm, float(np.mean(s_f != s_ref)))
+
+
+@pytest.mark.parametrize("shape,bits", [((5, 5, 128, 128, 2), 8), ((20, 2, 128, 128, 2), 4), ((3, 1, 12, 256, 2), 2),
+                                        ((2, 37, 8, 128, 2), 8)])
+def test_spiking_conv1_lif_tensor_tolerance(cuda_lib, oracle_lib, shape, bits):
+  """SNNQP_LIF_TENSOR: the tau = 2 leak of conv1 runs on the tensor core (tcgen05.mma scale-input-d, membranes in
+  TMEM, exact integer operands, per-channel compare multiplier).  Tolerance parity against the integer oracle (north star):
+  pooled spikes flip <= 1e-4, final membranes within 1e-5 of max(1, |u|) except on the (counted) neurons a flip
+  touched.  Shapes: 160 tiles (one full wave of the 148 persistent CTAs plus a ragged one), T = 20, two tiles per
+  image row (W = 256), fewer tiles than CTAs (74); u8 and bit-packed output, both batch layouts, extreme counts."""
+  T, B, H, W, Cin = shape
+  rng = np.random.default_rng(H * 7 + bits)
+  lay, q, bn, stt = make_layer(rng, 2, 128, bits, 0.3)
+  x = np.minimum(rng.poisson(0.3, size=shape), 255).astype(np.uint8)
+  x[0, 0, 0, 0, :] = 255; x[-1, -1, -1, -1, :] = 200
+  packed = pk_mod.pack_conv3x3(lay, bits, DEV, bn, stt)
+  s_ref, info = ref_int.spiking_conv3x3(x, q, *ref_int.fold_affine(lay["DuQ_0"]["c"], bits, bn, stt, 128),
+                                        pool=True, want=True)
+  assert 0.02 < s_ref.mean() < 0.9
+  for lm in (_lib.LIF_TENSOR,):
+    for bm in (True, False):
+      for yb in (True, False):
+        s, u, _ = run_conv(cuda_lib, x, packed.wq, packed.scale, packed.bias, 128, True, _lib.IMPL_TCGEN05,
+                           batch_major=bm, dumps="u", y_bits=yb, lif_mode=lm)
+        flips = int((s != s_ref).sum())
+        assert flips <= 1e-4 * s_ref.size, (lm, bm, yb, flips)
+        bad = np.abs(u - info["u"]) > 1e-5 * np.maximum(1.0, np.abs(info["u"]))
+        assert bad.sum() <= 4 + 4 * flips, (lm, bm, yb, int(bad.sum()), float(np.abs(u - info["u"]).max()))
+        s2, _, _ = run_conv(cuda_lib, x, packed.wq, packed.scale, packed.bias, 128, True, _lib.IMPL_TCGEN05,
+                            batch_major=bm, dumps=False, y_bits=yb, lif_mode=lm)
+        assert np.array_equal(s2, s), "production and membrane-dumping variants disagree"
+  # outside the kernel's envelope (no pool) the mode means the reference op order: bit-exact
+  s_np, info_np = ref_int.spiking_conv3x3(x[:, :1], q, *ref_int.fold_affine(lay["DuQ_0"]["c"], bits, bn, stt, 128),
+                                          pool=False, want=True)
+  s, u, acc = run_conv(cuda_lib, x[:, :1], packed.wq, packed.scale, packed.bias, 128, False, _lib.IMPL_TCGEN05,
+                       lif_mode=_lib.LIF_TENSOR)
+  assert np.array_equal(s, s_np) and np.array_equal(u, info_np["u"]) and np.array_equal(acc, info_np["acc"])
 
 
 @pytest.mark.parametrize("shape,bits,pool", [

@@ -9,8 +9,9 @@ from snnquantprune_b200 import CextNetEngine, pack_cextnet, synthetic
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 296
 n_it = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 T, H, C = 20, 128, 128
-v = synthetic.make_variables(bits=8, prune_percentage=0.5, T=T, H=H, seed=1)
-fr = torch.as_tensor(synthetic.make_frames(B, T, H, H, seed=0), device="cuda")
+STABLE = bool(int(os.environ.get('SNNQP_C1_STABLE', '0')))     # 1: the StableRNG weights / frames of the production-shape test
+v = synthetic.make_variables(bits=8, prune_percentage=0.5, T=T, H=H, seed=1, stable=STABLE)
+fr = torch.as_tensor(synthetic.make_frames(B, T, H, H, seed=77 if STABLE else 0, stable=STABLE), device="cuda")
 ref = None
 MODES = [int(x) for x in os.environ.get('SNNQP_C1_MODES', '0,101,102,103,2').split(',')]
 for bits in (False, True):
