@@ -36,8 +36,8 @@
 //
 // Pipeline: TMA (6 input rows x 288 B, zero-filled halo) -> 2 patch warps (u8 -> fp16 K-rows, 128-byte swizzle) -> MMA
 // warp (per slot and step 5 x (128 x 128 x 16): hi / lo pieces x two K-steps of the patch + the bias K-step) -> 16
-// epilogue warps.  The four slots of a tile rotate: while the epilogue works on slots 1-3 of step t the tensor core already integrates
-// slot 0 of step t + 1.
+// epilogue warps.  The slots of a tile rotate in two pairs (one mbarrier hand-off per pair): while the epilogue works on
+// slots 2-3 of step t the tensor core already integrates slots 0-1 of step t + 1.
 #include <cuda_fp16.h>
 
 #include <cstdio>
@@ -54,6 +54,7 @@ namespace {
 constexpr int kC = 128;
 constexpr int kTileQuads = 128, kQuadCols = 64;           // 2 quad rows x 64 quad columns
 constexpr int kSlots = 4, kSlotCols = 128;                // 32 channels x 4 quad positions per slot
+constexpr int kPairs = 2;                                 // hand-off unit between the MMA warp and the epilogue: two slots
 constexpr int kEpiWarps = 16, kPatchWarps = 2;
 constexpr int kThreads = (kEpiWarps + 2 + kPatchWarps) * 32;
 constexpr int kStRows = 6, kStRowBytes = 288, kStBytes = 1792;      // staging stage (1728 B used)
@@ -130,8 +131,8 @@ k_conv1_tclif(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
   uint64_t *bars = reinterpret_cast<uint64_t *>(st_smem + kStStages * kStBytes);
   uint64_t *st_full = bars, *st_empty = bars + kStStages;
   uint64_t *a_full = bars + 2 * kStStages, *a_empty = a_full + kAStages;
-  uint64_t *acc_full = a_empty + kAStages, *acc_empty = acc_full + kSlots;
-  uint32_t &tmem_slot = *reinterpret_cast<uint32_t *>(acc_empty + kSlots);
+  uint64_t *acc_full = a_empty + kAStages, *acc_empty = acc_full + kPairs;
+  uint32_t &tmem_slot = *reinterpret_cast<uint32_t *>(acc_empty + kPairs);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -185,7 +186,7 @@ k_conv1_tclif(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
     ptx::prefetch_tmap(&tmap_x);
     for (int i = 0; i < kStStages; ++i) { ptx::mbar_init(st_full + i, 1); ptx::mbar_init(st_empty + i, kPatchWarps); }
     for (int i = 0; i < kAStages; ++i) { ptx::mbar_init(a_full + i, kPatchWarps); ptx::mbar_init(a_empty + i, 1); }
-    for (int i = 0; i < kSlots; ++i) { ptx::mbar_init(acc_full + i, 1); ptx::mbar_init(acc_empty + i, kEpiWarps); }
+    for (int i = 0; i < kPairs; ++i) { ptx::mbar_init(acc_full + i, 1); ptx::mbar_init(acc_empty + i, kEpiWarps); }
     ptx::fence_barrier_init();
   }
   if (warp == kEpiWarps + 1) ptx::tmem_alloc<kTmemCols>(&tmem_slot);
@@ -229,8 +230,11 @@ k_conv1_tclif(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
           const uint64_t ad = ptx::make_desc_sw128(a_addr + as * kABytes, 0);
 #pragma unroll
           for (int sl = 0; sl < kSlots; ++sl) {
-            ptx::mbar_wait_suspend(acc_empty + sl, (step & 1) ^ 1, 20000u);     // the epilogue wrote step - 1's resets back
-            ptx::tc_fence_after();
+            // one hand-off per slot pair: the epilogue wrote step - 1's resets of both slots back
+            if ((sl & 1) == 0) {
+              ptx::mbar_wait_suspend(acc_empty + (sl >> 1), (step & 1) ^ 1, 20000u);
+              ptx::tc_fence_after();
+            }
             const uint32_t d = tmem_base + sl * kSlotCols;
             const uint64_t b0 = ptx::make_desc_sw128(w_addr + (2 * sl) * kWBlock, 0);
             const uint64_t b1 = ptx::make_desc_sw128(w_addr + (2 * sl + 1) * kWBlock, 0);
@@ -240,7 +244,7 @@ k_conv1_tclif(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
             mma_f16(d, ad, b0 + 4, idesc, 1);                     // lo pieces
             mma_f16(d, ad + 2, b0 + 6, idesc, 1);
             mma_f16(d, od, b1, idesc, 1);                         // + b
-            ptx::mma_commit(acc_full + sl);
+            if (sl & 1) ptx::mma_commit(acc_full + (sl >> 1));
           }
           ptx::mma_commit(a_empty + as);
         }
@@ -282,7 +286,9 @@ k_conv1_tclif(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
   } else {
     // ===================== epilogue: compare, reset (written back to TMEM), pool, pack =====================
     const int q = warp & 3, g = warp >> 2;              // TMEM lane quarter (32 quads), 32-column chunk = 8 channels
-    const uint32_t col0 = tmem_base + ((uint32_t)(q * 32) << 16) + 32 * g;
+    // (the OR-reduction of a warp-uniform value lands in a uniform register: tcgen05.ld / st take their address from one,
+    // and the compiler otherwise re-derives it with R2UR at every use)
+    const uint32_t col0 = __reduce_or_sync(0xffffffffu, tmem_base + ((uint32_t)(q * 32) << 16) + 32 * g);
     const int Wo = a.W / 2;
     const int qr = q >> 1, qc = (q & 1) * 32 + lane;    // this thread's quad inside the tile
     // 1.0f if un >= 1 else 0.0f.  The membrane domain is scaled by dom = 2^k: threshold dom for FSET; on the FMA pipe
@@ -329,11 +335,12 @@ k_conv1_tclif(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
             // next load: chunk 1 of this slot, or chunk 0 of the next slot-step once its MMAs have completed.  The
             // barrier is polled before the arithmetic and its answer used after it (the try_wait latency hides).
             const bool more = sl + 1 < kSlots || !(last_item && t + 1 == a.T);
-            uint64_t *nbar = acc_full + (sl + 1) % kSlots;
+            const bool cross = (sl & 1) != 0;                         // the next chunk belongs to the other slot pair
+            uint64_t *nbar = acc_full + ((sl + 1) % kSlots >> 1);
             const uint32_t nph = sl + 1 < kSlots ? ph : ph ^ 1;
             bool ready = true;
             if (h == 0) SNNQP_TMEM_LD_X16(col0 + sl * kSlotCols + 16, acc2[1]);
-            else if (more) ready = ptx::mbar_try_wait(nbar, nph);
+            else if (more && cross) ready = ptx::mbar_try_wait(nbar, nph);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const float ua = __uint_as_float(acc[4 * i]), ub = __uint_as_float(acc[4 * i + 1]);
@@ -364,13 +371,17 @@ k_conv1_tclif(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
             }
             SNNQP_TMEM_ST_X16(col0 + sl * kSlotCols + 16 * h, acc);
             if (h == 1) {
-              ptx::tc_wait_st();
-              ptx::tc_fence_before();
-              __syncwarp();
-              if (lane == 0) ptx::mbar_arrive(acc_empty + sl);
+              if (cross) {                 // both slots of the pair are written back: hand them to the MMA warp
+                ptx::tc_wait_st();
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(acc_empty + (sl >> 1));
+              }
               if (more) {
-                if (!ready) ptx::mbar_wait(nbar, nph);
-                ptx::tc_fence_after();
+                if (cross) {
+                  if (!ready) ptx::mbar_wait(nbar, nph);
+                  ptx::tc_fence_after();
+                }
                 SNNQP_TMEM_LD_X16(col0 + ((sl + 1) % kSlots) * kSlotCols, acc2[0]);
               }
             }
