@@ -34,6 +34,16 @@ def test_library_exports_every_declared_symbol():
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_binding_constants_match_the_header():
+  """The enum-like #defines the Python binding mirrors (spike layouts, LIF modes, implementations)."""
+  from snnquantprune_b200 import _lib
+  header = open(os.path.join(ROOT, "include", "snnqp.h")).read()
+  val = lambda name: int(re.search(rf"#define {name} (-?\d+)", header).group(1))
+  assert (_lib.LIF_EXACT, _lib.LIF_FAST, _lib.LIF_TENSOR) == (val("SNNQP_LIF_EXACT"), val("SNNQP_LIF_FAST"), val("SNNQP_LIF_TENSOR"))
+  assert (_lib.SPIKES_U8, _lib.SPIKES_BITS) == (val("SNNQP_SPIKES_U8"), val("SNNQP_SPIKES_BITS"))
+  assert (_lib.IMPL_AUTO, _lib.IMPL_SIMT, _lib.IMPL_TCGEN05) == (val("SNNQP_IMPL_AUTO"), val("SNNQP_IMPL_SIMT"), val("SNNQP_IMPL_TCGEN05"))
+
+
 def test_no_gpu_fails_loudly_not_silently():
   _build()
   from snnquantprune_b200 import _lib
