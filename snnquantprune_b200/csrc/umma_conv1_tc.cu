@@ -18,7 +18,7 @@
 // sat(un * 2^(24-k) + (1 - 2^24)) which is exactly 1 for un >= 1 and exactly 0 for the largest fp32 below 1.
 // What differs from the reference is where the roundings fall (w * s once per weight, then the tensor core's fp32
 // accumulation instead of one IEEE fma per neuron): measured against the reference-order kernel the final membranes
-// differ by 0.5 * 2^-24 on average (p99 3 * 2^-24, tools/probe_tclif_error.py) and 1e-8 .. 1.5e-7 of the pooled
+// differ by 0.7 * 2^-24 on average (p99 4, max 24 * 2^-24, tools/probe_tclif_error.py) and 1e-8 .. 1.5e-7 of the pooled
 // spikes flip depending on the weight set (profiles/r2_conv1_tclif.txt).  Tolerance parity (north star: membrane
 // 1e-5, spike flips <= 1e-4), not bit parity.
 // (Also tried: dividing by |s| per channel so the B operand is the integer weights -- three MMAs, exact operands, a
