@@ -36,8 +36,9 @@
 //
 // Pipeline: TMA (6 input rows x 288 B, zero-filled halo) -> 2 patch warps (u8 -> fp16 K-rows, 128-byte swizzle) -> MMA
 // warp (per slot and step 5 x (128 x 128 x 16): hi / lo pieces x two K-steps of the patch + the bias K-step) -> 16
-// epilogue warps.  The slots of a tile rotate in two pairs (one mbarrier hand-off per pair): while the epilogue works on
-// slots 2-3 of step t the tensor core already integrates slots 0-1 of step t + 1.
+// epilogue warps.  The slots of a tile rotate: the epilogue hands every slot back as soon as its resets are written
+// (the tensor core integrates step t + 1 of slot 0 while the epilogue is still on slots 1-3 of step t); the MMA warp
+// signals two slots at a time.
 #include <cuda_fp16.h>
 
 #include <cstdio>
@@ -54,7 +55,8 @@ namespace {
 constexpr int kC = 128;
 constexpr int kTileQuads = 128, kQuadCols = 64;           // 2 quad rows x 64 quad columns
 constexpr int kSlots = 4, kSlotCols = 128;                // 32 channels x 4 quad positions per slot
-constexpr int kPairs = 2;                                 // hand-off unit between the MMA warp and the epilogue: two slots
+constexpr int kPairs = 2;                                 // the MMA warp signals two slots at a time (acc_full); the epilogue
+                                                          // hands every slot back on its own (acc_empty) so the next step's MMAs start early
 constexpr int kEpiWarps = 16, kPatchWarps = 2;
 constexpr int kThreads = (kEpiWarps + 2 + kPatchWarps) * 32;
 constexpr int kStRows = 6, kStRowBytes = 288, kStBytes = 1792;      // staging stage (1728 B used)
@@ -132,7 +134,7 @@ k_conv1_tclif(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
   uint64_t *st_full = bars, *st_empty = bars + kStStages;
   uint64_t *a_full = bars + 2 * kStStages, *a_empty = a_full + kAStages;
   uint64_t *acc_full = a_empty + kAStages, *acc_empty = acc_full + kPairs;
-  uint32_t &tmem_slot = *reinterpret_cast<uint32_t *>(acc_empty + kPairs);
+  uint32_t &tmem_slot = *reinterpret_cast<uint32_t *>(acc_empty + kSlots);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -186,7 +188,8 @@ k_conv1_tclif(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
     ptx::prefetch_tmap(&tmap_x);
     for (int i = 0; i < kStStages; ++i) { ptx::mbar_init(st_full + i, 1); ptx::mbar_init(st_empty + i, kPatchWarps); }
     for (int i = 0; i < kAStages; ++i) { ptx::mbar_init(a_full + i, kPatchWarps); ptx::mbar_init(a_empty + i, 1); }
-    for (int i = 0; i < kPairs; ++i) { ptx::mbar_init(acc_full + i, 1); ptx::mbar_init(acc_empty + i, kEpiWarps); }
+    for (int i = 0; i < kPairs; ++i) ptx::mbar_init(acc_full + i, 1);
+    for (int i = 0; i < kSlots; ++i) ptx::mbar_init(acc_empty + i, kEpiWarps);
     ptx::fence_barrier_init();
   }
   if (warp == kEpiWarps + 1) ptx::tmem_alloc<kTmemCols>(&tmem_slot);
@@ -230,11 +233,8 @@ k_conv1_tclif(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
           const uint64_t ad = ptx::make_desc_sw128(a_addr + as * kABytes, 0);
 #pragma unroll
           for (int sl = 0; sl < kSlots; ++sl) {
-            // one hand-off per slot pair: the epilogue wrote step - 1's resets of both slots back
-            if ((sl & 1) == 0) {
-              ptx::mbar_wait_suspend(acc_empty + (sl >> 1), (step & 1) ^ 1, 20000u);
-              ptx::tc_fence_after();
-            }
+            ptx::mbar_wait_suspend(acc_empty + sl, (step & 1) ^ 1, 20000u);     // the epilogue wrote step - 1's resets back
+            ptx::tc_fence_after();
             const uint32_t d = tmem_base + sl * kSlotCols;
             const uint64_t b0 = ptx::make_desc_sw128(w_addr + (2 * sl) * kWBlock, 0);
             const uint64_t b1 = ptx::make_desc_sw128(w_addr + (2 * sl + 1) * kWBlock, 0);
@@ -371,12 +371,10 @@ k_conv1_tclif(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
             }
             SNNQP_TMEM_ST_X16(col0 + sl * kSlotCols + 16 * h, acc);
             if (h == 1) {
-              if (cross) {                 // both slots of the pair are written back: hand them to the MMA warp
-                ptx::tc_wait_st();
-                ptx::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(acc_empty + (sl >> 1));
-              }
+              ptx::tc_wait_st();             // the slot is written back: hand it to the MMA warp
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive(acc_empty + sl);
               if (more) {
                 if (cross) {
                   if (!ready) ptx::mbar_wait(nbar, nph);
