@@ -327,20 +327,22 @@ k_conv1_tclif(const __grid_constant__ CUtensorMap tmap_x, const TcArgs a) {
 #pragma unroll
         for (int sl = 0; sl < kSlots; ++sl) {
           uint32_t pooled[8];
+          bool ready = true;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             uint32_t (&acc)[16] = acc2[h];
             ptx::tc_wait_ld();                                       // this chunk's accumulators have landed
             SNNQP_REG_FENCE16(acc, 0);
             // next load: chunk 1 of this slot, or chunk 0 of the next slot-step once its MMAs have completed.  The
-            // barrier is polled before the arithmetic and its answer used after it (the try_wait latency hides).
+            // barrier is polled well before its answer is used (the try_wait latency, and part of a real wait, hide).
             const bool more = sl + 1 < kSlots || !(last_item && t + 1 == a.T);
             const bool cross = (sl & 1) != 0;                         // the next chunk belongs to the other slot pair
             uint64_t *nbar = acc_full + ((sl + 1) % kSlots >> 1);
             const uint32_t nph = sl + 1 < kSlots ? ph : ph ^ 1;
-            bool ready = true;
-            if (h == 0) SNNQP_TMEM_LD_X16(col0 + sl * kSlotCols + 16, acc2[1]);
-            else if (more && cross) ready = ptx::mbar_try_wait(nbar, nph);
+            if (h == 0) {
+              SNNQP_TMEM_LD_X16(col0 + sl * kSlotCols + 16, acc2[1]);
+              ready = !(more && cross) || ptx::mbar_try_wait(nbar, nph);       // polled a whole slot ahead of its use
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const float ua = __uint_as_float(acc[4 * i]), ub = __uint_as_float(acc[4 * i + 1]);
