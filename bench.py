@@ -484,7 +484,7 @@ def per_kernel_rooflines(eng, frames, ms_step, int8_peak_tops):
                         "algorithmic_mb_per_sample": mb},
                 "bound": "tensor" if tops / int8_peak_tops > gbs / hbm else "hbm",
                 "limiter": (("LIF_TENSOR: the leak runs on the tensor core (membranes in TMEM), the CUDA cores keep compare / reset / "
-                             "pool / pack: 3.09 issued instructions per neuron-step, issue active 64 %, tensor pipe 52 % "
+                             "pool / pack: 3.17 issued instructions per neuron-step, issue active 70 %, tensor pipe 56 % "
                              "(profiles/r2_ncu_full_lif_tensor.json)" if eng.lif_mode == 2 else
                              "issue slots of the LIF epilogue: 5.75 issued instructions per neuron-step, issue active 74 %, "
                              "tensor pipe 13 % (profiles/r2_ncu_full_final.json)") + " -- far from both rooflines by construction")

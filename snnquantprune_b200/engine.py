@@ -77,7 +77,7 @@ class CextNetEngine:
     (every other block always runs the reference's op order): LIF_EXACT = the reference's op order, bit-identical to
     the oracle; LIF_FAST = single-rounding fma on the CUDA cores (membranes within 1 ulp per step, 12 flipped spikes in
     3.1e9); LIF_TENSOR (default) = the leak runs on the tensor core (tcgen05.mma scale-input-d, membranes resident in
-    TMEM; csrc/umma_conv1_tc.cu): 39 % less conv1 time, tolerance parity -- 45 flipped spikes in 3.1e9 (1.5e-8; bar
+    TMEM; csrc/umma_conv1_tc.cu): 44 % less conv1 time, tolerance parity -- 45 flipped spikes in 3.1e9 (1.5e-8; bar
     1e-4), final membranes within 1e-5 (tools/time_conv1.py, tests/test_gpu_parity.py).  Outside the kernel's
     envelope (H = W = 128 multiples, standard LIF constants) LIF_TENSOR means LIF_EXACT."""
     self.pk = packed
