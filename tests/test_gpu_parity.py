@@ -211,13 +211,14 @@ def test_spiking_conv1_tcgen05_bit_exact(cuda_lib, oracle_lib, shape, bits, pool
 
 
 @pytest.mark.parametrize("shape,bits", [((5, 5, 128, 128, 2), 8), ((20, 2, 128, 128, 2), 4), ((3, 1, 12, 256, 2), 2),
-                                        ((2, 37, 8, 128, 2), 8)])
+                                        ((2, 37, 8, 128, 2), 8), ((1, 2, 4, 128, 2), 8)])
 def test_spiking_conv1_lif_tensor_tolerance(cuda_lib, oracle_lib, shape, bits):
   """SNNQP_LIF_TENSOR: the tau = 2 leak of conv1 runs on the tensor core (tcgen05.mma scale-input-d, membranes in
   TMEM, exact integer operands, per-channel compare multiplier).  Tolerance parity against the integer oracle (north star):
   pooled spikes flip <= 1e-4, final membranes within 1e-5 of max(1, |u|) except on the (counted) neurons a flip
   touched.  Shapes: 160 tiles (one full wave of the 148 persistent CTAs plus a ragged one), T = 20, two tiles per
-  image row (W = 256), fewer tiles than CTAs (74); u8 and bit-packed output, both batch layouts, extreme counts."""
+  image row (W = 256), fewer tiles than CTAs (74), a single step of a single tile row (T = 1, H = 4); u8 and bit-packed
+  output, both batch layouts, extreme counts."""
   T, B, H, W, Cin = shape
   rng = np.random.default_rng(H * 7 + bits)
   lay, q, bn, stt = make_layer(rng, 2, 128, bits, 0.3)
@@ -226,7 +227,7 @@ def test_spiking_conv1_lif_tensor_tolerance(cuda_lib, oracle_lib, shape, bits):
   packed = pk_mod.pack_conv3x3(lay, bits, DEV, bn, stt)
   s_ref, info = ref_int.spiking_conv3x3(x, q, *ref_int.fold_affine(lay["DuQ_0"]["c"], bits, bn, stt, 128),
                                         pool=True, want=True)
-  assert 0.02 < s_ref.mean() < 0.9
+  assert T == 1 or 0.02 < s_ref.mean() < 0.9
   for lm in (_lib.LIF_TENSOR,):
     for bm in (True, False):
       for yb in (True, False):
