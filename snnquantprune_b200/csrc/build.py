@@ -19,6 +19,10 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 # XLA FFI handlers (xla_ffi_shim.cc) compile for real where jaxlib's headers are: SNNQP_XLA_INCLUDE=<dir holding xla/ffi/api/ffi.h>
 XLA_INC = ["-I", os.environ["SNNQP_XLA_INCLUDE"]] if os.environ.get("SNNQP_XLA_INCLUDE") else []
+if os.environ.get("SNNQP_MMA_WARPS"):       # experiment: MMA-issuing warps of the 3x3 tile kernel (1 or 2)
+  FLAGS.append("-DSNNQP_MMA_WARPS=" + os.environ["SNNQP_MMA_WARPS"])
+if os.environ.get("SNNQP_T_TAPS"):          # experiment: weight taps of the 3x3 tile kernel resident in TMEM
+  FLAGS.append("-DSNNQP_T_TAPS=" + os.environ["SNNQP_T_TAPS"])
 if os.environ.get("SNNQP_C1_SUSPEND"):      # experiment: hardware-suspended producer waits in conv1 (tools/run_r2_gpu16.sh)
   FLAGS.append("-DSNNQP_C1_SUSPEND")
 if os.environ.get("SNNQP_EXP_WARPS"):       # experiment: number of expander warps of the bit-packed tile kernel

@@ -51,11 +51,21 @@ constexpr int kStageBytes = 23552;              // >= 180 rows * 128 B, 1024-ali
 constexpr int kEpiWarps = 16;
 constexpr int kRowsPerThread = kTileH / (kEpiWarps / 4);     // 4
 constexpr int kColsPerThread = kRowsPerThread * kTileW;      // 32 accumulator columns per thread
-constexpr int kThreads = (kEpiWarps + 2) * 32;  // + TMA warp + MMA warp
+// MMA issuers: a lone issuing thread needs ~72 cycles per tcgen05.mma next to the epilogue / expander warps of its SM
+// sub-partition (the MMA itself runs 64), so with two issuers each one owns every other step (= one of the two
+// accumulator buffers) and has two step times to issue its 36 MMAs (A/B: tools/run_r2_gpu35.sh).
+#ifndef SNNQP_MMA_WARPS
+#define SNNQP_MMA_WARPS 2
+#endif
+constexpr int kMmaWarps = SNNQP_MMA_WARPS;
+constexpr int kThreads = (kEpiWarps + 1 + kMmaWarps) * 32;  // + TMA warp + MMA warp(s); the second MMA warp is the CTA's last
 // Bit-packed input (SNNQP_SPIKES_BITS): TMA stages the packed tile (16 B per position), two expander warps turn
 // bits into the u8 K-major 128B-swizzled MMA operand (3 integer ops per 4 bytes: nibble * 0x00204081 & 0x01010101).
 #ifndef SNNQP_EXP_WARPS
 #define SNNQP_EXP_WARPS 3
+#endif
+#ifndef SNNQP_T_TAPS
+#define SNNQP_T_TAPS 7          // weight taps resident in TMEM (8 fills all 512 columns: A/B in tools/run_r2_gpu34.sh)
 #endif
 constexpr int kExpWarps = SNNQP_EXP_WARPS;   // 3 keeps the MMA issuer's SM sub-partition free of an expander warp (A/B: tools/run_r2_gpu17.sh)
 constexpr int kThreadsX = kThreads + kExpWarps * 32;
@@ -101,7 +111,7 @@ template <bool FAST, bool COUNTS, bool XBITS, bool POPC = false>
 __global__ void __launch_bounds__(XBITS ? kThreadsX : kThreads, 1)
 k_conv3x3_tile(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                const UmmaArgs a) {
-  constexpr int kTmemTaps = 7, kStages = XBITS ? kStagesBits : 4;
+  constexpr int kTmemTaps = SNNQP_T_TAPS, kStages = XBITS ? kStagesBits : 4;
   constexpr int kWSmemBytes = (9 - kTmemTaps) * kTapBytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -154,6 +164,7 @@ k_conv3x3_tile(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  constexpr int kMma1Warp = kEpiWarps + 2 + (XBITS ? kExpWarps : 0);      // (only with kMmaWarps == 2)
   if (warp == kEpiWarps) {
     // ===================== TMA producer =====================
     if (ptx::elect_one()) {
@@ -181,8 +192,9 @@ k_conv3x3_tile(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         }
       }
     }
-  } else if (warp == kEpiWarps + 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == kEpiWarps + 1 || (kMmaWarps == 2 && warp == kMma1Warp)) {
+    // ===================== MMA issuer(s) =====================
+    const uint32_t mma_id = warp == kEpiWarps + 1 ? 0u : 1u;
     // The leader is chosen with elect.sync: inside a plain `lane == 0` branch ptxas treats the region as divergent
     // and wraps every UTCIMMA in an ELECT / BRA.U.ANY serialisation loop (~18 instructions per MMA, measured
     // 112 cycles per 128x144x32 MMA instead of 72).
@@ -227,6 +239,7 @@ k_conv3x3_tile(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         for (int t = 0; t < a.T; ++t, ++step) {
           const uint32_t s = step & 1, ph = (step >> 1) & 1;
           const uint32_t si = step % kStages, phi = (step / kStages) & 1;
+          if (kMmaWarps == 2 && s != mma_id) continue;          // the other issuer's step (and accumulator buffer)
           ptx::mbar_wait(acc_empty + s, ph ^ 1);
           ptx::mbar_wait(in_full + si, phi);
           if constexpr (XBITS) {
@@ -287,7 +300,7 @@ k_conv3x3_tile(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         atomicAdd(&g_tile_skip_t[1], n_tiles);
       }
     }
-  } else if (warp >= kEpiWarps + 2) {
+  } else if (warp >= kEpiWarps + 2 && warp < kEpiWarps + 2 + kExpWarps) {
     // ===================== expanders (XBITS): packed bits -> u8 operand rows =====================
     if constexpr (XBITS) {
       const int et = threadIdx.x - (kEpiWarps + 2) * 32;          // 0 .. 32 * kExpWarps - 1
@@ -612,14 +625,14 @@ int launch_conv3x3_tile(const snnqp_block_params &p, const uint8_t *x, const int
                        "no u_final / acc_dump)");
 #define SNNQP_LAUNCH_TILE(FA, CO, XB)                                                                          \
   do {                                                                                                         \
-    constexpr int kSm = smem_bytes_for(7, XB ? kStagesBits : 4, XB);                                                              \
+    constexpr int kSm = smem_bytes_for(SNNQP_T_TAPS, XB ? kStagesBits : 4, XB);                                                              \
     if (int rc = ensure_smem_attr<k_conv3x3_tile<FA, CO, XB>>(kSm)) return rc;                                 \
     k_conv3x3_tile<FA, CO, XB><<<grid, XB ? kThreadsX : kThreads, kSm, st>>>(tmx, tmw, a);                     \
   } while (0)
   if (a.y_popcount) {
     if (!(xbits && fast && a.y_bits && !counts))
       return unsupported("tcgen05 conv: y_popcount needs bit-packed input and output, the production variant, no spike_counts");
-    constexpr int kSm = smem_bytes_for(7, kStagesBits, true);
+    constexpr int kSm = smem_bytes_for(SNNQP_T_TAPS, kStagesBits, true);
     if (int rc = ensure_smem_attr<k_conv3x3_tile<true, false, true, true>>(kSm)) return rc;
     k_conv3x3_tile<true, false, true, true><<<grid, kThreadsX, kSm, st>>>(tmx, tmw, a);
   } else if (xbits) {
