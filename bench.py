@@ -488,7 +488,7 @@ def per_kernel_rooflines(eng, frames, ms_step, int8_peak_tops):
                              "(profiles/r2_ncu_full_lif_tensor.json)" if eng.lif_mode == 2 else
                              "issue slots of the LIF epilogue: 5.75 issued instructions per neuron-step, issue active 74 %, "
                              "tensor pipe 13 % (profiles/r2_ncu_full_final.json)") + " -- far from both rooflines by construction")
-                           if "conv1" in name else "tensor pipe (89 % active bit-packed, 95 % with u8 spikes)"})
+                           if "conv1" in name else "tensor pipe (97 % active bit-packed, 99 % with u8 spikes; two MMA-issuing warps)"})
   return out
 
 
