@@ -160,7 +160,7 @@ typedef struct snnqp_block_params {
 /*   TENSOR (conv1, tcgen05 path, production variant only; EXACT elsewhere): the
  *          leak runs on the tensor core -- tcgen05.mma's scale-input-d computes
  *          D = A * B + D / 2, so the TMEM accumulator IS the membrane (scale
- *          folded into three bf16 weight pieces, bias on a constant-one K
+ *          folded into two fp16 weight pieces, bias on a constant-one K
  *          column) and the epilogue only compares, resets and packs.  The
  *          accumulation rounding is the tensor core's, not IEEE fma: tolerance
  *          parity (membrane 1e-5, spike flips <= 1e-4), not bit parity. */
